@@ -1,0 +1,382 @@
+// C ABI glue (include/aai.h): pitched device images, kernel dispatch, the host-buffer entry point with its
+// row-band partitioner over per-device streams.  CUDA runtime only -- no torch, no NCCL (bands are independent,
+// SURVEY.md §8e), no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "aai_internal.h"
+
+namespace {
+
+thread_local char g_error[512] = "";
+std::atomic<int64_t> g_launches{0};
+thread_local float g_h2d_ms = -1.f, g_kernel_ms = -1.f, g_d2h_ms = -1.f;
+
+size_t elem_size(int dtype) {
+    switch (dtype) {
+        case AAI_F64: return 8;
+        case AAI_F32: return 4;
+        case AAI_U8: return 1;
+        default: return 0;
+    }
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    aai_set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? AAI_ERR_NO_DEVICE : AAI_ERR_CUDA;
+}
+#define AAI_CUDA(call)                                   \
+    do {                                                 \
+        cudaError_t e_ = (call);                         \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+bool image_ok(const aai_image *im) {
+    return im && im->data && elem_size(im->dtype) && im->channels >= 1 && im->channels <= 4 && im->width > 0 &&
+           im->height > 0 && im->rows >= 0 && im->y0 >= 0 && im->y0 + im->rows <= im->height &&
+           im->pitch_bytes >= (int64_t)(im->width * im->channels * (int64_t)elem_size(im->dtype));
+}
+
+// grow-only per-device scratch images used by aai_run_host (avoids cudaMalloc/cudaFree per call)
+struct Workspace {
+    void *ptr[2] = {nullptr, nullptr};
+    size_t cap[2] = {0, 0};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::mutex busy;  // held for the duration of one band run on this device
+};
+constexpr int kMaxDevices = 64;
+std::mutex g_ws_mutex;
+Workspace g_ws[kMaxDevices];
+
+int workspace_get(int device, size_t bytes0, size_t bytes1, Workspace **out) {
+    if (device < 0 || device >= kMaxDevices) {
+        aai_set_error("device index %d out of range", device);
+        return AAI_ERR_ARGUMENT;
+    }
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    Workspace &w = g_ws[device];
+    AAI_CUDA(cudaSetDevice(device));
+    if (!w.stream) {
+        AAI_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+        for (auto &e : w.ev) AAI_CUDA(cudaEventCreate(&e));
+    }
+    const size_t need[2] = {bytes0, bytes1};
+    for (int k = 0; k < 2; ++k) {
+        if (w.cap[k] < need[k]) {
+            if (w.ptr[k]) AAI_CUDA(cudaFree(w.ptr[k]));
+            w.ptr[k] = nullptr;
+            w.cap[k] = 0;
+            AAI_CUDA(cudaMalloc(&w.ptr[k], need[k]));
+            w.cap[k] = need[k];
+        }
+    }
+    *out = &w;
+    return AAI_OK;
+}
+
+int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+void aai_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+}
+
+AaiKernelParams aai_make_kernel_params(const aai_plan &p, const aai_image &src, const aai_image &dst, int64_t row0,
+                                       int64_t row1) {
+    AaiKernelParams k;
+    std::memset(&k, 0, sizeof k);
+    k.side = p.side;
+    k.off_ix = p.off_ix;
+    k.off_iy = p.off_iy;
+    k.iso_x = p.iso_x;
+    k.iso_y = p.iso_y;
+    k.off_x = p.off_x;
+    k.off_y = p.off_y;
+    const double c = p.cos_t, s = p.sin_t, h = p.side / 2;
+    AaiShape &g = k.shape;
+    g.cs = c;
+    g.sn = s;
+    g.half = h;
+    g.hc = h * c;
+    g.hs = h * s;
+    g.k_sc = s / c;
+    g.k_hc = h / c;
+    g.k_cs = c / s;  // +inf when the reduced angle is exactly 0: the separable path never reads it
+    g.k_hs = h / s;
+    g.inv_c = 1.0 / c;
+    g.inv_s = 1.0 / s;
+    g.m = (c + s) / 2;
+    g.thr = std::fabs(c - s) / 2;
+    k.reach = p.reach;
+    k.hb = h * (c + s);
+    k.mod_w = (int32_t)p.mod_w;
+    k.mod_h = (int32_t)p.mod_h;
+    k.dst_w = (int32_t)p.dst_w;
+    k.dst_h = (int32_t)p.dst_h;
+    k.scale = (int32_t)p.scale;
+    k.quadrant = p.quadrant;
+    k.src = src.data;
+    k.src_pitch = src.pitch_bytes;
+    k.src_w = (int32_t)src.width;
+    k.src_h = (int32_t)src.height;
+    k.src_y0 = (int32_t)src.y0;
+    k.src_rows = (int32_t)src.rows;
+    k.channels = src.channels;
+    k.dst = dst.data;
+    k.dst_pitch = dst.pitch_bytes;
+    k.dst_y0 = (int32_t)dst.y0;
+    k.row0 = (int32_t)row0;
+    k.row1 = (int32_t)row1;
+    return k;
+}
+
+extern "C" {
+
+const char *aai_last_error(void) { return g_error; }
+
+int64_t aai_launch_count(void) { return g_launches.load(); }
+
+int aai_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int aai_image_alloc(aai_image *img, int device, int64_t width, int64_t height, int64_t y0, int64_t rows,
+                    int32_t dtype, int32_t channels) {
+    if (!img || !elem_size(dtype) || channels < 1 || channels > 4 || width <= 0 || height <= 0 || rows < 0 ||
+        y0 < 0 || y0 + rows > height) {
+        aai_set_error("aai_image_alloc: bad argument");
+        return AAI_ERR_ARGUMENT;
+    }
+    AAI_CUDA(cudaSetDevice(device));
+    std::memset(img, 0, sizeof *img);
+    img->width = width;
+    img->height = height;
+    img->y0 = y0;
+    img->rows = rows;
+    img->dtype = dtype;
+    img->channels = channels;
+    // rows start on 512-byte boundaries: satisfies TMA's 16-byte global stride rule and 128-bit accesses
+    img->pitch_bytes = round_up(width * channels * (int64_t)elem_size(dtype), 512);
+    const size_t bytes = (size_t)img->pitch_bytes * (size_t)(rows > 0 ? rows : 1);
+    AAI_CUDA(cudaMalloc(&img->data, bytes));
+    return AAI_OK;
+}
+
+int aai_image_free(aai_image *img, int device) {
+    if (!img) return AAI_ERR_ARGUMENT;
+    if (img->data) {
+        AAI_CUDA(cudaSetDevice(device));
+        AAI_CUDA(cudaFree(img->data));
+    }
+    img->data = nullptr;
+    return AAI_OK;
+}
+
+static int copy_rows(const aai_image *dst, const aai_image *src, cudaMemcpyKind kind, int device, void *stream) {
+    // copies the rows of the image that holds FEWER rows (the device band) from/to the other one
+    if (!image_ok(dst) || !image_ok(src) || dst->width != src->width || dst->height != src->height ||
+        dst->dtype != src->dtype || dst->channels != src->channels) {
+        aai_set_error("aai_image copy: incompatible images");
+        return AAI_ERR_ARGUMENT;
+    }
+    const aai_image *band = (kind == cudaMemcpyHostToDevice) ? dst : src;
+    const aai_image *full = (kind == cudaMemcpyHostToDevice) ? src : dst;
+    if (band->y0 < full->y0 || band->y0 + band->rows > full->y0 + full->rows) {
+        aai_set_error("aai_image copy: band rows [%lld,%lld) not inside [%lld,%lld)", (long long)band->y0,
+                      (long long)(band->y0 + band->rows), (long long)full->y0, (long long)(full->y0 + full->rows));
+        return AAI_ERR_ARGUMENT;
+    }
+    if (band->rows == 0) return AAI_OK;
+    AAI_CUDA(cudaSetDevice(device));
+    const size_t row_bytes = (size_t)(band->width * band->channels) * elem_size(band->dtype);
+    const char *s = (const char *)src->data + (kind == cudaMemcpyHostToDevice ? (band->y0 - src->y0) * src->pitch_bytes : 0);
+    char *d = (char *)dst->data + (kind == cudaMemcpyDeviceToHost ? (band->y0 - dst->y0) * dst->pitch_bytes : 0);
+    AAI_CUDA(cudaMemcpy2DAsync(d, (size_t)dst->pitch_bytes, s, (size_t)src->pitch_bytes, row_bytes,
+                               (size_t)band->rows, kind, (cudaStream_t)stream));
+    return AAI_OK;
+}
+
+int aai_image_upload(const aai_image *device_img, const aai_image *host_img, int device, void *stream) {
+    return copy_rows(device_img, host_img, cudaMemcpyHostToDevice, device, stream);
+}
+int aai_image_download(const aai_image *host_img, const aai_image *device_img, int device, void *stream) {
+    return copy_rows(host_img, device_img, cudaMemcpyDeviceToHost, device, stream);
+}
+
+int aai_run_device(const aai_plan *plan, int mode, int arith, const aai_image *src, const aai_image *dst,
+                   int64_t row0, int64_t row1, int device, void *stream) {
+    if (!plan) {
+        aai_set_error("aai_run_device: null plan");
+        return AAI_ERR_ARGUMENT;
+    }
+    if (plan->status != AAI_OK) return plan->status;
+    if (!image_ok(src) || !image_ok(dst) || src->width != plan->src_w || src->height != plan->src_h ||
+        dst->width != plan->dst_w || dst->height != plan->dst_h || src->channels != dst->channels) {
+        aai_set_error("aai_run_device: images do not match the plan (src %lldx%lld, canvas %lldx%lld)",
+                      (long long)plan->src_w, (long long)plan->src_h, (long long)plan->dst_w, (long long)plan->dst_h);
+        return AAI_ERR_ARGUMENT;
+    }
+    if (mode != AAI_MODE_AREA_AVERAGE && mode != AAI_MODE_FAST) {
+        aai_set_error("aai_run_device: interpolation mode must be 1 or 2");
+        return AAI_ERR_ARGUMENT;
+    }
+    if (arith != AAI_ARITH_F64 && arith != AAI_ARITH_F32) {
+        aai_set_error("aai_run_device: unknown arithmetic %d", arith);
+        return AAI_ERR_ARGUMENT;
+    }
+    if (row0 < 0 || row1 > plan->dst_h || row0 > row1 || row0 < dst->y0 || row1 > dst->y0 + dst->rows) {
+        aai_set_error("aai_run_device: rows [%lld,%lld) outside the destination band", (long long)row0, (long long)row1);
+        return AAI_ERR_ARGUMENT;
+    }
+    if (row0 == row1) return AAI_OK;
+    int64_t sx0, sx1, sy0, sy1;
+    aai_band_source_window(plan, row0, row1, &sx0, &sx1, &sy0, &sy1);
+    if (sy1 > sy0 && (sy0 < src->y0 || sy1 > src->y0 + src->rows)) {
+        aai_set_error("aai_run_device: source rows [%lld,%lld) needed, [%lld,%lld) present", (long long)sy0,
+                      (long long)sy1, (long long)src->y0, (long long)(src->y0 + src->rows));
+        return AAI_ERR_ARGUMENT;
+    }
+    AAI_CUDA(cudaSetDevice(device));
+    const AaiKernelParams kp = aai_make_kernel_params(*plan, *src, *dst, row0, row1);
+    int e;
+    if (mode == AAI_MODE_FAST)
+        e = aai_launch_fast(kp, src->dtype, dst->dtype, stream);
+    else if (plan->axis_aligned)
+        e = aai_launch_separable(kp, arith, src->dtype, dst->dtype, stream);
+    else
+        e = aai_launch_overlap(kp, arith, src->dtype, dst->dtype, stream);
+    g_launches.fetch_add(1);
+    if (e != (int)cudaSuccess) return cuda_fail((cudaError_t)e, "kernel launch");
+    return AAI_OK;
+}
+
+int aai_run_host(const aai_plan *plan, int mode, int arith, const aai_image *src, const aai_image *dst,
+                 const int *devices, int n_devices) {
+    if (!plan) {
+        aai_set_error("aai_run_host: null plan");
+        return AAI_ERR_ARGUMENT;
+    }
+    if (plan->status != AAI_OK) return plan->status;
+    if (!image_ok(src) || !image_ok(dst) || src->y0 != 0 || src->rows != src->height || dst->y0 != 0 ||
+        dst->rows != dst->height || src->width != plan->src_w || src->height != plan->src_h ||
+        dst->width != plan->dst_w || dst->height != plan->dst_h || src->channels != dst->channels) {
+        aai_set_error("aai_run_host: host images must be whole images matching the plan");
+        return AAI_ERR_ARGUMENT;
+    }
+    const int dev0 = 0;
+    if (!devices || n_devices <= 0) {
+        devices = &dev0;
+        n_devices = 1;
+    }
+    const int have = aai_device_count();
+    if (have <= 0) {
+        aai_set_error("aai_run_host: no CUDA device; this library has no CPU fallback");
+        return AAI_ERR_NO_DEVICE;
+    }
+    for (int k = 0; k < n_devices; ++k)
+        if (devices[k] < 0 || devices[k] >= have) {
+            aai_set_error("aai_run_host: device %d not present (%d devices)", devices[k], have);
+            return AAI_ERR_ARGUMENT;
+        }
+    std::vector<int64_t> bounds((size_t)n_devices + 1);
+    int rc = aai_partition_rows(plan, n_devices, bounds.data());
+    if (rc != AAI_OK) return rc;
+
+    std::vector<int> status((size_t)n_devices, AAI_OK);
+    std::vector<std::string> messages((size_t)n_devices);
+    std::vector<float> t_h2d((size_t)n_devices, 0.f), t_k((size_t)n_devices, 0.f), t_d2h((size_t)n_devices, 0.f);
+
+    auto run_band = [&](int k) -> int {
+        const int device = devices[k];
+        const int64_t row0 = bounds[(size_t)k], row1 = bounds[(size_t)k + 1];
+        if (row1 <= row0) return AAI_OK;
+        int64_t sx0, sx1, sy0, sy1;
+        aai_band_source_window(plan, row0, row1, &sx0, &sx1, &sy0, &sy1);
+        aai_image dsrc = *src, ddst = *dst;
+        dsrc.y0 = sy0;
+        dsrc.rows = sy1 - sy0;
+        dsrc.pitch_bytes = round_up(src->width * src->channels * (int64_t)elem_size(src->dtype), 512);
+        ddst.y0 = row0;
+        ddst.rows = row1 - row0;
+        ddst.pitch_bytes = round_up(dst->width * dst->channels * (int64_t)elem_size(dst->dtype), 512);
+        Workspace *w = nullptr;
+        std::lock_guard<std::mutex> busy(g_ws[(device >= 0 && device < kMaxDevices) ? device : 0].busy);
+        int r = workspace_get(device, (size_t)dsrc.pitch_bytes * (size_t)(dsrc.rows > 0 ? dsrc.rows : 1),
+                              (size_t)ddst.pitch_bytes * (size_t)ddst.rows, &w);
+        if (r != AAI_OK) return r;
+        dsrc.data = w->ptr[0];
+        ddst.data = w->ptr[1];
+        AAI_CUDA(cudaEventRecord(w->ev[0], w->stream));
+        if (dsrc.rows > 0) {
+            r = aai_image_upload(&dsrc, src, device, w->stream);
+            if (r != AAI_OK) return r;
+        }
+        AAI_CUDA(cudaEventRecord(w->ev[1], w->stream));
+        r = aai_run_device(plan, mode, arith, &dsrc, &ddst, row0, row1, device, w->stream);
+        if (r != AAI_OK) return r;
+        AAI_CUDA(cudaEventRecord(w->ev[2], w->stream));
+        r = aai_image_download(dst, &ddst, device, w->stream);
+        if (r != AAI_OK) return r;
+        AAI_CUDA(cudaEventRecord(w->ev[3], w->stream));
+        AAI_CUDA(cudaStreamSynchronize(w->stream));
+        AAI_CUDA(cudaEventElapsedTime(&t_h2d[(size_t)k], w->ev[0], w->ev[1]));
+        AAI_CUDA(cudaEventElapsedTime(&t_k[(size_t)k], w->ev[1], w->ev[2]));
+        AAI_CUDA(cudaEventElapsedTime(&t_d2h[(size_t)k], w->ev[2], w->ev[3]));
+        return AAI_OK;
+    };
+
+    if (n_devices == 1) {
+        status[0] = run_band(0);
+        if (status[0] != AAI_OK) return status[0];
+    } else {
+        // one host thread per device: pageable-memory copies block their issuing thread
+        std::vector<std::thread> pool;
+        for (int k = 0; k < n_devices; ++k)
+            pool.emplace_back([&, k]() {
+                status[(size_t)k] = run_band(k);
+                if (status[(size_t)k] != AAI_OK) messages[(size_t)k] = g_error;
+            });
+        for (auto &t : pool) t.join();
+        for (int k = 0; k < n_devices; ++k)
+            if (status[(size_t)k] != AAI_OK) {
+                aai_set_error("device %d: %s", devices[k], messages[(size_t)k].c_str());
+                return status[(size_t)k];
+            }
+    }
+    g_h2d_ms = g_kernel_ms = g_d2h_ms = 0.f;
+    for (int k = 0; k < n_devices; ++k) {
+        g_h2d_ms = std::fmax(g_h2d_ms, t_h2d[(size_t)k]);
+        g_kernel_ms = std::fmax(g_kernel_ms, t_k[(size_t)k]);
+        g_d2h_ms = std::fmax(g_d2h_ms, t_d2h[(size_t)k]);
+    }
+    return AAI_OK;
+}
+
+int aai_last_host_timing(float *h2d_ms, float *kernel_ms, float *d2h_ms) {
+    if (g_kernel_ms < 0.f) return AAI_ERR_ARGUMENT;
+    if (h2d_ms) *h2d_ms = g_h2d_ms;
+    if (kernel_ms) *kernel_ms = g_kernel_ms;
+    if (d2h_ms) *d2h_ms = g_d2h_ms;
+    return AAI_OK;
+}
+
+}  // extern "C"

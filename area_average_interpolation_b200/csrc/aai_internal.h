@@ -1,0 +1,41 @@
+// Internal declarations shared by the host plan, the C ABI glue and the CUDA kernels.
+#ifndef AAI_INTERNAL_H_
+#define AAI_INTERNAL_H_
+
+#include <cstdint>
+#include <vector>
+
+#include "../../include/aai.h"
+#include "aai_cell.cuh"
+
+// Everything a kernel needs, passed by value (__grid_constant__).  Built on the host in FP64 from the plan.
+struct AaiKernelParams {
+    // canvas-pixel centre expression of Source.cpp:212-219
+    double side, off_ix, off_iy, iso_x, iso_y, off_x, off_y;
+    AaiShape shape;   // cos/sin, h = L/2 and the derived footprint constants (aai_cell.cuh)
+    double reach;     // L*sqrt(2)/2 (search window, 426-429)
+    double hb;        // h*(c+s): half extent of the footprint's axis-aligned bounding box
+    int32_t mod_w, mod_h, dst_w, dst_h;
+    int32_t scale, quadrant;
+    // source view (original frame): rows [src_y0, src_y0+src_rows) are present
+    const void *src;
+    int64_t src_pitch;
+    int32_t src_w, src_h, src_y0, src_rows;
+    int32_t channels;
+    // destination band view: rows [dst_y0, dst_y0+dst_rows) are present; rows [row0,row1) are computed
+    void *dst;
+    int64_t dst_pitch;
+    int32_t dst_y0, row0, row1;
+};
+
+AaiKernelParams aai_make_kernel_params(const aai_plan &plan, const aai_image &src, const aai_image &dst,
+                                       int64_t row0, int64_t row1);
+
+// kernel launchers (aai_kernels.cu); return the cudaError_t of the launch as int
+int aai_launch_overlap(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);
+int aai_launch_separable(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);
+int aai_launch_fast(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
+
+void aai_set_error(const char *fmt, ...);
+
+#endif  // AAI_INTERNAL_H_

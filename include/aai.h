@@ -1,0 +1,166 @@
+/*
+ * aai.h -- C ABI of the B200-native area-average interpolation hot path.
+ *
+ * This is the drop-in boundary for the ONE operator of Ishikawa-lab/Area_average_interpolation that this
+ * repository accelerates:
+ *
+ *     pair<bool,string> AreaAverageInterpolation::areaAverageInterpolation(
+ *         IMG src, IMG &dst, dP srcResolution, dP dstResolution,
+ *         dP srcIsocenter, dP &dstIsocenter, double rotationAngle)            (Source.cpp:55-583)
+ *
+ * (and, as the "next" row f1, its unweighted sibling fastAreaAverageInterpolation, Source.cpp:584-911).
+ * A C caller cannot receive a callee-sized std::vector, so the reference call is split into
+ *   1. aai_plan_create()  -- everything the reference decides before its main loop
+ *                            (validation 112-132, expansion/quadrant 139-176, canvas geometry 177-200),
+ *                            i.e. the output size, the returned dstIsocenter and the error string;
+ *   2. aai_run_host() / aai_run_device() -- the main loop 411-579 on the GPU(s).
+ * The C++ host mirror with the reference's exact signature lives in
+ * area_average_interpolation_b200/csrc/aai.hpp; the Python mirror in area_average_interpolation_b200/.
+ *
+ * Plain C types only; no STL, no torch types.  Every function is thread-safe for distinct plans/buffers.
+ * There is NO CPU fallback: the run functions fail with AAI_ERR_CUDA when no sm_100a device is usable.
+ */
+#ifndef AAI_H_
+#define AAI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AAI_VERSION 100
+
+/* Status codes.  1..4 are the reference's four validation failures, in the order it tests them
+ * (Source.cpp:112, 118, 123, 128); aai_status_string() returns the reference's message verbatim. */
+enum {
+    AAI_OK = 0,
+    AAI_ERR_RESOLUTION_XY = 1,  /* "Assumed X & Y resolution are same."                          (115) */
+    AAI_ERR_RESOLUTION_NONPOS = 2, /* "0 or negative resolution is not acceptable."              (120) */
+    AAI_ERR_NO_ROWS = 3,        /* "There is no data in src array."                              (125) */
+    AAI_ERR_NO_COLUMNS = 4,     /* "There is no data in the second dimension of src array."      (130) */
+    /* beyond the reference (it loops forever / reads out of bounds on these): */
+    AAI_ERR_ANGLE = 5,          /* rotation angle is NaN or infinite (reference: endless loop at 141-142) */
+    AAI_ERR_ARGUMENT = 6,       /* null pointer, bad dtype / channel count / band, image too large */
+    AAI_ERR_CUDA = 7,           /* CUDA runtime / driver failure; see aai_last_error() */
+    AAI_ERR_NO_DEVICE = 8       /* no usable CUDA device (there is no CPU fallback) */
+};
+
+/* Element types of pitched images. */
+enum { AAI_F64 = 0, AAI_F32 = 1, AAI_U8 = 2 };
+
+/* Interpolation mode = the reference's `interpolationMode` user setting (Source.cpp:1534). */
+enum {
+    AAI_MODE_AREA_AVERAGE = 1, /* areaAverageInterpolation      (Source.cpp:55)  -- the north-star path */
+    AAI_MODE_FAST = 2          /* fastAreaAverageInterpolation  (Source.cpp:584) */
+};
+
+/* Arithmetic of the overlap kernel. */
+enum {
+    AAI_ARITH_F64 = 0, /* geometry, areas and accumulation in double (<= 1e-9 relative vs the reference) */
+    AAI_ARITH_F32 = 1  /* geometry + shape decisions in double, area polynomials + accumulation in float */
+};
+
+/*
+ * The geometry plan: the ~30 scalars the reference derives before its main loop.  POD, immutable after
+ * aai_plan_create(), shared by every band / device so that N-GPU results are bitwise identical to 1 GPU.
+ */
+typedef struct aai_plan {
+    int32_t status;     /* AAI_OK or 1..5 */
+    uint32_t scale;     /* integer source expansion S (Source.cpp:139) */
+    int32_t quadrant;   /* beforehandRotationMode k in 0..3 (140-146) */
+    int32_t axis_aligned; /* 1 when the reduced angle is exactly axis-aligned (separable path) */
+    int64_t src_w, src_h; /* original source size */
+    int64_t mod_w, mod_h; /* expanded + quadrant-rotated source size (150-156) */
+    int64_t dst_w, dst_h; /* canvas size (179-180) */
+    double theta_deg;   /* reduced angle in [0,90) */
+    double sin_t, cos_t; /* (147-148) */
+    double iso_x, iso_y; /* isocentre in expanded coordinates (173-174) */
+    double ratio;       /* expansionRatio (177) */
+    double side;        /* dstSideLength L: footprint side in expanded pixels (178) */
+    double dst_iso_x, dst_iso_y; /* the reference's OUT parameter dstIsocenter (185-186) */
+    double off_ix, off_iy; /* dstIsocenterOffset (183-184) */
+    double off_x, off_y;   /* canvas offset (187-200) */
+    double reach;       /* L*sqrt(2)/2: half-diagonal used by the search window (426-429) */
+} aai_plan;
+
+/* A pitched image (or a horizontal band of one) in host or device memory.
+ * Row y of the full image, y0 <= y < y0+rows, starts at (char*)data + (y - y0)*pitch_bytes and holds
+ * width*channels interleaved elements of `dtype`.  Full images have y0 = 0, rows = height. */
+typedef struct aai_image {
+    void *data;
+    int64_t pitch_bytes;
+    int64_t width, height; /* of the FULL image */
+    int64_t y0, rows;      /* rows present in `data` */
+    int32_t dtype;         /* AAI_F64 / AAI_F32 / AAI_U8 */
+    int32_t channels;      /* 1..4 interleaved channels sharing one geometry */
+} aai_image;
+
+/* ---- plan ---------------------------------------------------------------------------------------------- */
+
+/* Replaces Source.cpp:112-200.  Arguments are the reference's (src.front().size(), src.size(),
+ * srcResolution, dstResolution, srcIsocenter, rotationAngle).  Returns plan->status. */
+int aai_plan_create(int64_t src_w, int64_t src_h, double src_res_x, double src_res_y, double dst_res_x,
+                    double dst_res_y, double src_iso_x, double src_iso_y, double angle_deg, aai_plan *plan);
+
+/* The reference's ret.second for status 0..4 ("" for AAI_OK); a description for the other codes. */
+const char *aai_status_string(int status);
+
+/* Message of the last AAI_ERR_CUDA / AAI_ERR_ARGUMENT on the calling thread. */
+const char *aai_last_error(void);
+
+/* ---- row-band partitioner (host logic, no GPU needed) ---------------------------------------- */
+
+/* Splits canvas rows [0, dst_h) into n_parts contiguous bands balanced by COVERED pixels (canvas corners of a
+ * rotated image are empty).  bounds[0..n_parts] receives the band limits. */
+int aai_partition_rows(const aai_plan *plan, int n_parts, int64_t *bounds);
+
+/* Source rows/columns (in ORIGINAL source coordinates, half-open) that canvas rows [row0,row1) can touch:
+ * the band's halo. */
+int aai_band_source_window(const aai_plan *plan, int64_t row0, int64_t row1, int64_t *src_x0, int64_t *src_x1,
+                           int64_t *src_y0, int64_t *src_y1);
+
+/* Number of canvas pixels in rows [row0,row1) whose search window meets the source (the rest are written as 0). */
+int64_t aai_covered_pixels(const aai_plan *plan, int64_t row0, int64_t row1);
+
+/* ---- pitched device images ----------------------------------------------------------------------------- */
+
+int aai_device_count(void);
+
+/* Allocates rows [y0, y0+rows) of a width x height x channels image on `device` (cudaMallocPitch layout,
+ * pitch a multiple of 512 bytes so that every row is TMA- and 128-bit aligned). */
+int aai_image_alloc(aai_image *img, int device, int64_t width, int64_t height, int64_t y0, int64_t rows,
+                    int32_t dtype, int32_t channels);
+int aai_image_free(aai_image *img, int device);
+/* Copies the rows the device image holds from / to a host image that holds at least those rows. */
+int aai_image_upload(const aai_image *device_img, const aai_image *host_img, int device, void *stream);
+int aai_image_download(const aai_image *host_img, const aai_image *device_img, int device, void *stream);
+
+/* ---- the hot path --------------------------------------------------------------------------------------- */
+
+/* Main loop of the reference (Source.cpp:411-579 / 866-907) for canvas rows [row0,row1) on one device.
+ * `src` must hold the rows reported by aai_band_source_window() (or the whole image); `dst` must hold rows
+ * [row0,row1) (or the whole canvas).  Both are DEVICE images on `device`.  Asynchronous on `stream`
+ * (a cudaStream_t; NULL = the default stream); returns after enqueueing. */
+int aai_run_device(const aai_plan *plan, int mode, int arith, const aai_image *src, const aai_image *dst,
+                   int64_t row0, int64_t row1, int device, void *stream);
+
+/* The reference call end to end with HOST buffers: upload (each device gets its band's halo), kernels on
+ * per-device streams, download.  `devices` = NULL / n_devices = 0 means device 0.  No NCCL: bands are
+ * independent.  Blocks until dst is complete. */
+int aai_run_host(const aai_plan *plan, int mode, int arith, const aai_image *src, const aai_image *dst,
+                 const int *devices, int n_devices);
+
+/* Kernel-launch counter of this process (every overlap / separable / fast kernel launch increments it). */
+int64_t aai_launch_count(void);
+
+/* Device-side breakdown [ms] of the last aai_run_host() on this thread, from CUDA events on the per-device
+ * streams (max over devices): host->device copies, kernels, device->host copies.  Returns AAI_OK or
+ * AAI_ERR_ARGUMENT if no run has completed. */
+int aai_last_host_timing(float *h2d_ms, float *kernel_ms, float *d2h_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AAI_H_ */
