@@ -102,6 +102,9 @@ def lib() -> C.CDLL:
         L.aai_run_host.restype = C.c_int
         L.aai_run_host.argtypes = [C.POINTER(Plan), C.c_int, C.c_int, C.POINTER(Image), C.POINTER(Image),
                                    C.POINTER(C.c_int), C.c_int]
+        L.aai_run_host_band.restype = C.c_int
+        L.aai_run_host_band.argtypes = [C.POINTER(Plan), C.c_int, C.c_int, C.POINTER(Image), C.POINTER(Image),
+                                        C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int]
         L.aai_launch_count.restype = C.c_int64
         L.aai_last_host_timing.restype = C.c_int
         L.aai_last_host_timing.argtypes = [C.POINTER(C.c_float)] * 3
@@ -225,6 +228,13 @@ def run_host(plan: Plan, src: np.ndarray, dst: np.ndarray, mode: int = MODE_AREA
     _check(lib().aai_run_host(C.byref(plan), int(mode), int(arith), C.byref(si), C.byref(di), arr, n))
 
 
+def run_host_band(plan: Plan, src_img: Image, dst_img: Image, row0: int, row1: int, mode: int = MODE_AREA_AVERAGE,
+                  arith: int = ARITH_F64, device: int = 0, stream: int = 0, synchronize: bool = True) -> None:
+    """``aai_run_host_band``: one rank's share of the host-buffer call (halo upload, kernels, band download)."""
+    _check(lib().aai_run_host_band(C.byref(plan), int(mode), int(arith), C.byref(src_img), C.byref(dst_img),
+                                   int(row0), int(row1), int(device), C.c_void_p(stream), int(bool(synchronize))))
+
+
 @dataclass
 class Result:
     ok: bool
@@ -284,5 +294,5 @@ class AreaAverageInterpolation:
 __all__ = [
     "AreaAverageInterpolation", "Result", "Plan", "Image", "AaiError", "make_plan", "partition_rows",
     "band_source_window", "covered_pixels", "device_count", "launch_count", "last_host_timing", "run_device",
-    "run_host", "tensor_image", "status_string", "last_error", "lib", "LIB_PATH",
+    "run_host", "run_host_band", "tensor_image", "status_string", "last_error", "lib", "LIB_PATH",
 ]

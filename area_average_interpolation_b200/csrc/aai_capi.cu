@@ -269,19 +269,80 @@ int aai_run_device(const aai_plan *plan, int mode, int arith, const aai_image *s
     return AAI_OK;
 }
 
-int aai_run_host(const aai_plan *plan, int mode, int arith, const aai_image *src, const aai_image *dst,
-                 const int *devices, int n_devices) {
+static int check_host_images(const char *who, const aai_plan *plan, const aai_image *src, const aai_image *dst,
+                             bool whole) {
     if (!plan) {
-        aai_set_error("aai_run_host: null plan");
+        aai_set_error("%s: null plan", who);
         return AAI_ERR_ARGUMENT;
     }
     if (plan->status != AAI_OK) return plan->status;
-    if (!image_ok(src) || !image_ok(dst) || src->y0 != 0 || src->rows != src->height || dst->y0 != 0 ||
-        dst->rows != dst->height || src->width != plan->src_w || src->height != plan->src_h ||
+    if (!image_ok(src) || !image_ok(dst) || src->width != plan->src_w || src->height != plan->src_h ||
         dst->width != plan->dst_w || dst->height != plan->dst_h || src->channels != dst->channels) {
-        aai_set_error("aai_run_host: host images must be whole images matching the plan");
+        aai_set_error("%s: host images do not match the plan", who);
         return AAI_ERR_ARGUMENT;
     }
+    if (whole && (src->y0 != 0 || src->rows != src->height || dst->y0 != 0 || dst->rows != dst->height)) {
+        aai_set_error("%s: whole host images expected", who);
+        return AAI_ERR_ARGUMENT;
+    }
+    return AAI_OK;
+}
+
+int aai_run_host_band(const aai_plan *plan, int mode, int arith, const aai_image *src, const aai_image *dst,
+                      int64_t row0, int64_t row1, int device, void *stream, int synchronize) {
+    int r = check_host_images("aai_run_host_band", plan, src, dst, false);
+    if (r != AAI_OK) return r;
+    if (row0 < 0 || row1 > plan->dst_h || row0 > row1) {
+        aai_set_error("aai_run_host_band: bad rows [%lld,%lld)", (long long)row0, (long long)row1);
+        return AAI_ERR_ARGUMENT;
+    }
+    if (row1 == row0) return AAI_OK;
+    if (aai_device_count() <= device || device < 0) {
+        aai_set_error("aai_run_host_band: device %d not present; this library has no CPU fallback", device);
+        return aai_device_count() <= 0 ? AAI_ERR_NO_DEVICE : AAI_ERR_ARGUMENT;
+    }
+    int64_t sx0, sx1, sy0, sy1;
+    aai_band_source_window(plan, row0, row1, &sx0, &sx1, &sy0, &sy1);
+    aai_image dsrc = *src, ddst = *dst;
+    dsrc.y0 = sy0;
+    dsrc.rows = sy1 - sy0;
+    dsrc.pitch_bytes = round_up(src->width * src->channels * (int64_t)elem_size(src->dtype), 512);
+    ddst.y0 = row0;
+    ddst.rows = row1 - row0;
+    ddst.pitch_bytes = round_up(dst->width * dst->channels * (int64_t)elem_size(dst->dtype), 512);
+    std::lock_guard<std::mutex> busy(g_ws[device < kMaxDevices ? device : 0].busy);
+    Workspace *w = nullptr;
+    r = workspace_get(device, (size_t)dsrc.pitch_bytes * (size_t)(dsrc.rows > 0 ? dsrc.rows : 1),
+                      (size_t)ddst.pitch_bytes * (size_t)ddst.rows, &w);
+    if (r != AAI_OK) return r;
+    dsrc.data = w->ptr[0];
+    ddst.data = w->ptr[1];
+    cudaStream_t st = stream ? (cudaStream_t)stream : w->stream;
+    AAI_CUDA(cudaEventRecord(w->ev[0], st));
+    if (dsrc.rows > 0) {
+        r = aai_image_upload(&dsrc, src, device, st);
+        if (r != AAI_OK) return r;
+    }
+    AAI_CUDA(cudaEventRecord(w->ev[1], st));
+    r = aai_run_device(plan, mode, arith, &dsrc, &ddst, row0, row1, device, st);
+    if (r != AAI_OK) return r;
+    AAI_CUDA(cudaEventRecord(w->ev[2], st));
+    r = aai_image_download(dst, &ddst, device, st);
+    if (r != AAI_OK) return r;
+    AAI_CUDA(cudaEventRecord(w->ev[3], st));
+    if (synchronize || !stream) {
+        AAI_CUDA(cudaStreamSynchronize(st));
+        AAI_CUDA(cudaEventElapsedTime(&g_h2d_ms, w->ev[0], w->ev[1]));
+        AAI_CUDA(cudaEventElapsedTime(&g_kernel_ms, w->ev[1], w->ev[2]));
+        AAI_CUDA(cudaEventElapsedTime(&g_d2h_ms, w->ev[2], w->ev[3]));
+    }
+    return AAI_OK;
+}
+
+int aai_run_host(const aai_plan *plan, int mode, int arith, const aai_image *src, const aai_image *dst,
+                 const int *devices, int n_devices) {
+    int rc = check_host_images("aai_run_host", plan, src, dst, true);
+    if (rc != AAI_OK) return rc;
     const int dev0 = 0;
     if (!devices || n_devices <= 0) {
         devices = &dev0;
@@ -298,70 +359,30 @@ int aai_run_host(const aai_plan *plan, int mode, int arith, const aai_image *src
             return AAI_ERR_ARGUMENT;
         }
     std::vector<int64_t> bounds((size_t)n_devices + 1);
-    int rc = aai_partition_rows(plan, n_devices, bounds.data());
+    rc = aai_partition_rows(plan, n_devices, bounds.data());
     if (rc != AAI_OK) return rc;
+    if (n_devices == 1) return aai_run_host_band(plan, mode, arith, src, dst, 0, plan->dst_h, devices[0], nullptr, 1);
 
+    // one host thread per device: pageable-memory copies block their issuing thread
     std::vector<int> status((size_t)n_devices, AAI_OK);
     std::vector<std::string> messages((size_t)n_devices);
     std::vector<float> t_h2d((size_t)n_devices, 0.f), t_k((size_t)n_devices, 0.f), t_d2h((size_t)n_devices, 0.f);
-
-    auto run_band = [&](int k) -> int {
-        const int device = devices[k];
-        const int64_t row0 = bounds[(size_t)k], row1 = bounds[(size_t)k + 1];
-        if (row1 <= row0) return AAI_OK;
-        int64_t sx0, sx1, sy0, sy1;
-        aai_band_source_window(plan, row0, row1, &sx0, &sx1, &sy0, &sy1);
-        aai_image dsrc = *src, ddst = *dst;
-        dsrc.y0 = sy0;
-        dsrc.rows = sy1 - sy0;
-        dsrc.pitch_bytes = round_up(src->width * src->channels * (int64_t)elem_size(src->dtype), 512);
-        ddst.y0 = row0;
-        ddst.rows = row1 - row0;
-        ddst.pitch_bytes = round_up(dst->width * dst->channels * (int64_t)elem_size(dst->dtype), 512);
-        Workspace *w = nullptr;
-        std::lock_guard<std::mutex> busy(g_ws[(device >= 0 && device < kMaxDevices) ? device : 0].busy);
-        int r = workspace_get(device, (size_t)dsrc.pitch_bytes * (size_t)(dsrc.rows > 0 ? dsrc.rows : 1),
-                              (size_t)ddst.pitch_bytes * (size_t)ddst.rows, &w);
-        if (r != AAI_OK) return r;
-        dsrc.data = w->ptr[0];
-        ddst.data = w->ptr[1];
-        AAI_CUDA(cudaEventRecord(w->ev[0], w->stream));
-        if (dsrc.rows > 0) {
-            r = aai_image_upload(&dsrc, src, device, w->stream);
-            if (r != AAI_OK) return r;
+    std::vector<std::thread> pool;
+    for (int k = 0; k < n_devices; ++k)
+        pool.emplace_back([&, k]() {
+            status[(size_t)k] = aai_run_host_band(plan, mode, arith, src, dst, bounds[(size_t)k],
+                                                  bounds[(size_t)k + 1], devices[k], nullptr, 1);
+            if (status[(size_t)k] != AAI_OK) messages[(size_t)k] = g_error;
+            t_h2d[(size_t)k] = g_h2d_ms;
+            t_k[(size_t)k] = g_kernel_ms;
+            t_d2h[(size_t)k] = g_d2h_ms;
+        });
+    for (auto &t : pool) t.join();
+    for (int k = 0; k < n_devices; ++k)
+        if (status[(size_t)k] != AAI_OK) {
+            aai_set_error("device %d: %s", devices[k], messages[(size_t)k].c_str());
+            return status[(size_t)k];
         }
-        AAI_CUDA(cudaEventRecord(w->ev[1], w->stream));
-        r = aai_run_device(plan, mode, arith, &dsrc, &ddst, row0, row1, device, w->stream);
-        if (r != AAI_OK) return r;
-        AAI_CUDA(cudaEventRecord(w->ev[2], w->stream));
-        r = aai_image_download(dst, &ddst, device, w->stream);
-        if (r != AAI_OK) return r;
-        AAI_CUDA(cudaEventRecord(w->ev[3], w->stream));
-        AAI_CUDA(cudaStreamSynchronize(w->stream));
-        AAI_CUDA(cudaEventElapsedTime(&t_h2d[(size_t)k], w->ev[0], w->ev[1]));
-        AAI_CUDA(cudaEventElapsedTime(&t_k[(size_t)k], w->ev[1], w->ev[2]));
-        AAI_CUDA(cudaEventElapsedTime(&t_d2h[(size_t)k], w->ev[2], w->ev[3]));
-        return AAI_OK;
-    };
-
-    if (n_devices == 1) {
-        status[0] = run_band(0);
-        if (status[0] != AAI_OK) return status[0];
-    } else {
-        // one host thread per device: pageable-memory copies block their issuing thread
-        std::vector<std::thread> pool;
-        for (int k = 0; k < n_devices; ++k)
-            pool.emplace_back([&, k]() {
-                status[(size_t)k] = run_band(k);
-                if (status[(size_t)k] != AAI_OK) messages[(size_t)k] = g_error;
-            });
-        for (auto &t : pool) t.join();
-        for (int k = 0; k < n_devices; ++k)
-            if (status[(size_t)k] != AAI_OK) {
-                aai_set_error("device %d: %s", devices[k], messages[(size_t)k].c_str());
-                return status[(size_t)k];
-            }
-    }
     g_h2d_ms = g_kernel_ms = g_d2h_ms = 0.f;
     for (int k = 0; k < n_devices; ++k) {
         g_h2d_ms = std::fmax(g_h2d_ms, t_h2d[(size_t)k]);

@@ -1,0 +1,46 @@
+"""Work assignment for one-process-per-GPU runs: no collective on the data path.
+
+* one large image  -> contiguous canvas row bands balanced by covered pixels (``aai_partition_rows``) plus the
+  source halo each band needs (``aai_band_source_window``);
+* a batch of images -> whole images, contiguous blocks per rank.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Tuple
+
+from . import Plan, band_source_window, covered_pixels, partition_rows
+
+
+@dataclass(frozen=True)
+class Band:
+    rank: int
+    row0: int
+    row1: int
+    src_x0: int
+    src_x1: int
+    src_y0: int
+    src_y1: int
+    covered: int
+
+    @property
+    def rows(self) -> int:
+        return self.row1 - self.row0
+
+
+def band_for_rank(plan: Plan, rank: int, world_size: int) -> Band:
+    bounds = partition_rows(plan, world_size)
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    x0, x1, y0, y1 = band_source_window(plan, r0, r1)
+    return Band(rank, r0, r1, x0, x1, y0, y1, covered_pixels(plan, r0, r1))
+
+
+def all_bands(plan: Plan, world_size: int) -> List[Band]:
+    return [band_for_rank(plan, r, world_size) for r in range(world_size)]
+
+
+def batch_slice(n_images: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous block of whole images for ``rank`` (sizes differ by at most one)."""
+    base, extra = divmod(n_images, world_size)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)

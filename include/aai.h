@@ -152,6 +152,14 @@ int aai_run_device(const aai_plan *plan, int mode, int arith, const aai_image *s
 int aai_run_host(const aai_plan *plan, int mode, int arith, const aai_image *src, const aai_image *dst,
                  const int *devices, int n_devices);
 
+/* One band of the host-buffer call on one device: uploads the band's source halo, runs the kernels, downloads
+ * canvas rows [row0,row1) into `dst` (host images; each may hold just the band's halo / the band itself).  With `stream` = NULL an internal per-device stream
+ * is used and the call blocks; otherwise the work is enqueued on `stream` (a cudaStream_t) and the call returns
+ * without waiting unless `synchronize` is non-zero (use pinned host memory for truly asynchronous copies).
+ * This is what one rank of a one-process-per-GPU launch calls. */
+int aai_run_host_band(const aai_plan *plan, int mode, int arith, const aai_image *src, const aai_image *dst,
+                      int64_t row0, int64_t row1, int device, void *stream, int synchronize);
+
 /* Kernel-launch counter of this process (every overlap / separable / fast kernel launch increments it). */
 int64_t aai_launch_count(void);
 

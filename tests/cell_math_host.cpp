@@ -18,3 +18,28 @@ extern "C" void aai_test_pair_areas(double c, double s, double L, const double *
     const AaiShape g = make_shape(c, s, L);
     for (long long k = 0; k < n; ++k) out[k] = aai_pair_area(g, cx[k], cy[k], i[k], j[k]);
 }
+
+// Whole-image evaluation with the device arithmetic (FP64 kernel logic restated for the host), TEST ONLY.
+extern "C" void aai_test_image_f64(double c, double s, double L, double offIx, double offIy, double isoX, double isoY,
+                                   double offX, double offY, int modW, int modH, int dstW, int dstH,
+                                   const double *mod /* modH x modW */, double *out) {
+    const AaiShape g = make_shape(c, s, L);
+    const double reach = L * std::sqrt(2) / 2, hb = g.half * (c + s), ext = hb + 0.5 + 1e-9;
+    for (int y = 0; y < dstH; ++y)
+        for (int x = 0; x < dstW; ++x) {
+            const double u = ((x + offIx) * L - isoX) + offX, v = ((y + offIy) * L - isoY) + offY;
+            const double cx = (u * c + v * s) + isoX, cy = (-u * s + v * c) + isoY;
+            int wx0 = std::max(0, (int)std::floor(cx - reach - 1)), wx1 = std::min((int)std::ceil(cx + reach + 1), modW - 1);
+            int wy0 = std::max(0, (int)std::floor(cy - reach - 1)), wy1 = std::min((int)std::ceil(cy + reach + 1), modH - 1);
+            int ix0 = std::max(wx0, (int)std::ceil(cx - ext)), ix1 = std::min(wx1, (int)std::floor(cx + ext));
+            int jy0 = std::max(wy0, (int)std::ceil(cy - ext)), jy1 = std::min(wy1, (int)std::floor(cy + ext));
+            double sumA = 0, acc = 0;
+            for (int j = jy0; j <= jy1; ++j)
+                for (int i = ix0; i <= ix1; ++i) {
+                    const double a = aai_pair_area(g, cx, cy, i, j);
+                    sumA += a;
+                    acc += mod[(size_t)j * modW + i] * a;
+                }
+            out[(size_t)y * dstW + x] = 2.220446049250313e-16 < std::fabs(sumA) ? acc / sumA : 0.0;
+        }
+}

@@ -1,0 +1,87 @@
+"""CPU: the kernels' per-cell closed form (csrc/aai_cell.cuh, compiled for the host by tests/cell_math_host.cpp)
+against the oracle's literal shape classifier, pair by pair.  This is the arithmetic the GPU executes."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def cellmath(built):
+    out_dir = os.path.join(HERE, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libcellmath.so")
+    cxx = os.environ.get("CXX", "g++")
+    subprocess.run([cxx, "-O2", "-fPIC", "-shared", "-o", so, os.path.join(HERE, "cell_math_host.cpp")], check=True)
+    lib = C.CDLL(so)
+    lib.aai_test_pair_areas.argtypes = [C.c_double] * 3 + [C.c_void_p] * 5 + [C.c_longlong]
+    return lib
+
+
+def _vertices(cx, cy, c, s, h):
+    eu, ev = np.array([c, -s]), np.array([s, c])
+    ctr = np.array([cx, cy])
+    return np.array([ctr - h * eu - h * ev, ctr + h * eu - h * ev, ctr - h * eu + h * ev, ctr + h * eu + h * ev])
+
+
+@pytest.mark.parametrize("theta,side", [(30.0, 2.7027027), (17.3, 2.7027027), (45.0, 1.7647059), (61.0, 1.7391304),
+                                        (1.0, 5.5), (89.0, 3.3), (73.0, 9.0909), (44.999, 2.0), (12.0, 1.41422)])
+def test_cell_area_matches_oracle_shapes(cellmath, theta, side):
+    from oracle import port
+
+    rng = np.random.default_rng(int(theta * 1000) + 5)
+    c, s = np.cos(np.radians(theta)), np.sin(np.radians(theta))
+    n = 3000
+    cx, cy = rng.uniform(10, 20, n), rng.uniform(10, 20, n)
+    i = np.floor(cx + rng.uniform(-side, side, n)).astype(np.int32)
+    j = np.floor(cy + rng.uniform(-side, side, n)).astype(np.int32)
+    got = np.zeros(n)
+    cellmath.aai_test_pair_areas(c, s, side, cx.ctypes.data, cy.ctypes.data, i.ctypes.data, j.ctypes.data,
+                                 got.ctypes.data, n)
+    want = np.array([port.pair_area(_vertices(cx[k], cy[k], c, s, side / 2), int(i[k]), int(j[k])) for k in range(n)])
+    assert (want > 0).sum() > n // 5  # the sample really exercises touched cells
+    assert np.abs(got - want).max() < 1e-11
+
+
+def test_reference_quirk_is_reproduced(cellmath):
+    """A left/right edge cutting one corner must give 1/2 (1-a)(1-b), not the true 1/2 a b (Source.cpp:1055-1062)."""
+    from oracle import port
+
+    theta, side = 30.0, 2.7027027
+    c, s = np.cos(np.radians(theta)), np.sin(np.radians(theta))
+    rng = np.random.default_rng(99)
+    n = 20000
+    cx, cy = rng.uniform(10, 20, n), rng.uniform(10, 20, n)
+    i = np.floor(cx + rng.uniform(-side, side, n)).astype(np.int32)
+    j = np.floor(cy + rng.uniform(-side, side, n)).astype(np.int32)
+    got = np.zeros(n)
+    cellmath.aai_test_pair_areas(c, s, side, cx.ctypes.data, cy.ctypes.data, i.ctypes.data, j.ctypes.data,
+                                 got.ctypes.data, n)
+    # exact polygon clipping for comparison
+    def exact(k):
+        poly = [(i[k] - .5, j[k] - .5), (i[k] + .5, j[k] - .5), (i[k] + .5, j[k] + .5), (i[k] - .5, j[k] + .5)]
+        for (nx, ny) in [(c, -s), (-c, s), (s, c), (-s, -c)]:
+            out = []
+            for a in range(len(poly)):
+                p, q = poly[a], poly[(a + 1) % len(poly)]
+                dp = side / 2 - ((p[0] - cx[k]) * nx + (p[1] - cy[k]) * ny)
+                dq = side / 2 - ((q[0] - cx[k]) * nx + (q[1] - cy[k]) * ny)
+                if dp >= 0:
+                    out.append(p)
+                if (dp >= 0) != (dq >= 0):
+                    t = dp / (dp - dq)
+                    out.append((p[0] + t * (q[0] - p[0]), p[1] + t * (q[1] - p[1])))
+            poly = out
+            if not poly:
+                return 0.0
+        return 0.5 * abs(sum(poly[a][0] * poly[(a + 1) % len(poly)][1] - poly[(a + 1) % len(poly)][0] * poly[a][1]
+                             for a in range(len(poly))))
+    ex = np.array([exact(k) for k in range(2000)])
+    differs = np.abs(got[:2000] - ex) > 1e-9
+    assert 0.05 < differs.mean() < 0.5  # a sizeable share of touched pairs carries the quirk
+    want = np.array([port.pair_area(_vertices(cx[k], cy[k], c, s, side / 2), int(i[k]), int(j[k])) for k in range(2000)])
+    assert np.abs(got[:2000] - want).max() < 1e-11

@@ -1,0 +1,313 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI (libaai_b200.so), against the golden vectors of the
+compiled reference, against the CPU oracle on seeded inputs, and -- at BASELINE.json's full sizes -- through
+size-independent properties plus oracle-checked sample rows."""
+import numpy as np
+import pytest
+
+from common import TOL_F64_REL, TOL_F32_REL, TOL_U8_ABS, golden_source, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def aai(built):
+    import area_average_interpolation_b200 as m
+
+    assert m.device_count() >= 1, "no CUDA device: the product has no CPU fallback"
+    return m
+
+
+@pytest.fixture(scope="module")
+def oracle(built):
+    from oracle import port
+
+    return port
+
+
+def _run(aai, src, sres, dres, iso, angle, mode=1, arith=0, out_dtype=np.float64, devices=None):
+    op = aai.AreaAverageInterpolation(arith=arith, out_dtype=out_dtype, devices=devices)
+    f = op.areaAverageInterpolation if mode == 1 else op.fastAreaAverageInterpolation
+    before = aai.launch_count()
+    r = f(src, sres, dres, iso, angle)
+    assert r.ok, r.message
+    assert aai.launch_count() > before, "no CUDA kernel was launched"
+    return r
+
+
+# ---- golden vectors of the compiled reference ----------------------------------------------------------------
+
+def test_golden_vectors_f64(aai):
+    z, meta = load_golden()
+    for case in meta["cases"]:
+        src = golden_source(case)
+        r = _run(aai, src, case["src_res"], case["dst_res"], case["iso"], case["angle"], mode=case["mode"])
+        want = z[case["name"]]
+        assert list(r.dst.shape) == case["dst_shape"], case["name"]
+        assert list(r.dst_isocenter) == case["dst_iso"], case["name"]
+        if case.get("degenerate"):
+            continue  # compared under the conditioning mask below
+        err = rel_err(r.dst, want)
+        assert err.max() <= TOL_F64_REL, (case["name"], float(err.max()), int((err > TOL_F64_REL).sum()))
+
+
+def _conditioning_mask(oracle, src, case, want, delta=1e-11):
+    """T5: pixels on which the reference's own answer changes when the isocentre moves by 1e-11 (8 directions)."""
+    mask = np.zeros(want.shape, dtype=bool)
+    for dx, dy in [(1, 1), (-1, -1), (1, 0), (0, 1), (-1, 0), (0, -1), (1, -1), (-1, 1)]:
+        iso = (case["iso"][0] + dx * delta, case["iso"][1] + dy * delta)
+        st, moved, _ = oracle.run(src, case["src_res"], case["dst_res"], iso, case["angle"], mode=case["mode"])
+        mask |= rel_err(moved, want) > TOL_F64_REL
+    return mask
+
+
+def test_degenerate_inputs_match_outside_the_reference_conditioning_mask(aai, oracle):
+    """T4: vertices/edges exactly on grid lines.  Every pixel on which the reference is well conditioned must match;
+    the ill-conditioned ones (reference flips under a 1e-11 isocentre shift) are counted, not gated."""
+    z, meta = load_golden()
+    cases = [c for c in meta["cases"] if c.get("degenerate")]
+    assert len(cases) >= 2
+    for case in cases:
+        src = golden_source(case)
+        want = z[case["name"]]
+        r = _run(aai, src, case["src_res"], case["dst_res"], case["iso"], case["angle"], mode=case["mode"])
+        mask = _conditioning_mask(oracle, src, case, want)
+        err = rel_err(r.dst, want)
+        assert mask.mean() < 0.1, case["name"]
+        assert (err[~mask] <= TOL_F64_REL).all(), (case["name"], int(((err > TOL_F64_REL) & ~mask).sum()))
+        print(f"{case['name']}: {int(mask.sum())} ill-conditioned reference pixels of {mask.size} masked; "
+              f"{int((err[mask] > TOL_F64_REL).sum())} of them differ")
+
+
+def test_golden_vectors_axis_aligned_are_exact_on_u8(aai):
+    # 0.5x / 0 deg on 8-bit data: weights 1/2, 1, 1/2 (or the aligned 2x2 box) -> every operation is exact
+    z, meta = load_golden()
+    for name in ("cfg1_u8_half_0deg", "cfg1_u8_half_0deg_halfiso"):
+        case = next(c for c in meta["cases"] if c["name"] == name)
+        r = _run(aai, golden_source(case), case["src_res"], case["dst_res"], case["iso"], case["angle"])
+        assert np.array_equal(r.dst, z[name]), name
+
+
+def test_validation_failures_do_not_touch_the_gpu(aai):
+    _, meta = load_golden()
+    op = aai.AreaAverageInterpolation()
+    for e in meta["errors"]:
+        src = np.ones((e["h"], e["w"])) if e["h"] and e["w"] else np.zeros((e["h"], e["w"]))
+        before = aai.launch_count()
+        r = op.areaAverageInterpolation(src, e["src_res"], e["dst_res"], (1.0, 1.0), 10.0, dstIsocenter=(-7.0, -9.0))
+        assert (r.ok, r.message, list(r.dst_isocenter)) == (False, e["message"], e["dst_iso"]), e["name"]
+        assert aai.launch_count() == before
+
+
+# ---- oracle on seeded inputs ------------------------------------------------------------------------------------
+
+SWEEP = [
+    # w, h, ratio, angle, iso
+    (512, 512, 0.37, 17.3, (256.0, 256.0)),   # cfg4 replica
+    (512, 512, 0.37, 30.0, (256.0, 256.0)),   # cfg2 replica (integer isocentre: well conditioned)
+    (192, 192, 1.7, 45.0, (95.5, 95.5)),      # cfg3 replica (scale 3, half-integer isocentre)
+    (512, 512, 0.5, 0.0, (256.0, 256.0)),     # cfg1 / cfg5 replica
+    (300, 200, 0.11, 73.0, (150.0, 100.0)),   # strong downscale: L = 9.09, theta >= 45 branch
+    (257, 129, 0.37, 117.3, (100.0, 64.0)),   # quadrant 1, non-square
+    (129, 257, 0.45, 200.0, (64.0, 128.0)),   # quadrant 2
+    (150, 150, 0.9, 305.5, (0.0, 0.0)),       # quadrant 3, scale 2, isocentre at the corner
+    (64, 64, 2.3, 61.0, (32.0, 32.0)),        # scale 4
+    (200, 120, 0.2, -12.0, (400.0, -50.0)),   # isocentre far outside the image
+    (128, 128, 0.6, 89.0, (64.0, 64.0)),      # nearly 90 degrees
+    (128, 128, 0.6, 1.0, (64.0, 64.0)),       # nearly 0 degrees
+    (100, 100, 1.0, 180.0, (50.0, 50.0)),     # scale 2, axis aligned
+    (100, 80, 0.5, 270.0, (49.5, 40.5)),      # axis aligned, quadrant 3, half-integer isocentre
+    (90, 90, 0.70710678, 33.0, (45.0, 45.0)), # ratio*sqrt(2) just below 1
+    (31, 17, 0.3, 45.0, (15.2, 8.1)),         # canvas smaller than one tile
+]
+
+
+@pytest.mark.parametrize("w,h,ratio,angle,iso", SWEEP)
+def test_f64_kernel_matches_oracle(aai, oracle, w, h, ratio, angle, iso):
+    rng = np.random.default_rng(w * 7919 + h)
+    src = rng.uniform(0.0, 4096.0, size=(h, w))
+    r = _run(aai, src, 1.0, ratio, iso, angle)
+    st, want, wiso = oracle.run(src, 1.0, ratio, iso, angle)
+    assert st == 0 and want.shape == r.dst.shape and wiso == r.dst_isocenter
+    err = rel_err(r.dst, want)
+    assert err.max() <= TOL_F64_REL, (float(err.max()), int((err > TOL_F64_REL).sum()))
+
+
+@pytest.mark.parametrize("w,h,ratio,angle,iso", SWEEP[:8])
+def test_fast_mode_matches_oracle(aai, oracle, w, h, ratio, angle, iso):
+    rng = np.random.default_rng(w * 31 + h)
+    src = rng.uniform(0.0, 4096.0, size=(h, w))
+    r = _run(aai, src, 1.0, ratio, iso, angle, mode=2)
+    st, want, _ = oracle.run(src, 1.0, ratio, iso, angle, mode=2)
+    assert st == 0 and want.shape == r.dst.shape
+    assert rel_err(r.dst, want).max() <= TOL_F64_REL
+
+
+def test_u8_rgb_and_f32_sources(aai, oracle):
+    rng = np.random.default_rng(5)
+    rgb = rng.integers(0, 256, size=(120, 160, 3), dtype=np.uint8)
+    r = _run(aai, rgb, 1.0, 1.7, (79.5, 59.5), 45.0)
+    assert r.dst.shape[2] == 3
+    for c in range(3):
+        st, want, _ = oracle.run(rgb, 1.0, 1.7, (79.5, 59.5), 45.0, channel=c)
+        assert np.abs(r.dst[..., c] - want).max() <= TOL_U8_ABS
+        assert rel_err(r.dst[..., c], want).max() <= TOL_F64_REL
+    f32 = rng.uniform(0, 4096, size=(200, 150)).astype(np.float32)
+    r = _run(aai, f32, 1.0, 0.37, (75.0, 100.0), 17.3)
+    st, want, _ = oracle.run(f32, 1.0, 0.37, (75.0, 100.0), 17.3)
+    assert rel_err(r.dst, want).max() <= TOL_F64_REL
+    # float32 / uint8 destinations: the stored value is the rounded real-valued result
+    r32 = _run(aai, f32, 1.0, 0.37, (75.0, 100.0), 17.3, out_dtype=np.float32)
+    assert np.array_equal(r32.dst, want.astype(np.float32)) or rel_err(r32.dst, want).max() <= 1e-6
+    g8 = rng.integers(0, 256, size=(90, 90), dtype=np.uint8)
+    r8 = _run(aai, g8, 1.0, 0.37, (45.0, 45.0), 30.0, out_dtype=np.uint8)
+    st, want8, _ = oracle.run(g8, 1.0, 0.37, (45.0, 45.0), 30.0)
+    # documented store rule: round half up, saturate; ties are measure-zero on this input
+    assert np.abs(r8.dst.astype(np.float64) - np.floor(want8 + 0.5)).max() <= 1.0
+    assert (r8.dst.astype(np.float64) != np.floor(want8 + 0.5)).mean() < 1e-3
+
+
+def test_row_bands_are_bitwise_identical_to_one_launch(aai):
+    """T6: any band split (the multi-GPU partition) reproduces the single-launch result bit for bit."""
+    import torch
+
+    from area_average_interpolation_b200.sharding import all_bands
+
+    w, h, ratio, angle, iso = 700, 500, 0.37, 17.3, (350.0, 250.0)
+    plan = aai.make_plan(w, h, 1.0, ratio, iso, angle)
+    src = torch.rand(h, w, dtype=torch.float64, device="cuda") * 4096
+    whole = torch.empty(plan.dst_h, plan.dst_w, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    aai.run_device(plan, aai.tensor_image(src), aai.tensor_image(whole), stream=stream)
+    for n in (2, 3, 8):
+        parts = []
+        for band in all_bands(plan, n):
+            # the rank holds only its halo rows of the source and only its band of the canvas
+            halo = src[band.src_y0:band.src_y1].contiguous()
+            out = torch.full((band.rows, plan.dst_w), -1.0, dtype=torch.float64, device="cuda")
+            aai.run_device(plan, aai.tensor_image(halo, y0=band.src_y0, height=h),
+                           aai.tensor_image(out, y0=band.row0, height=plan.dst_h), band.row0, band.row1,
+                           stream=stream)
+            parts.append(out)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat(parts, 0), whole), n
+
+
+def test_multi_device_host_path_if_available(aai, oracle):
+    n = aai.device_count()
+    rng = np.random.default_rng(8)
+    src = rng.uniform(0, 4096, size=(300, 400))
+    one = _run(aai, src, 1.0, 0.37, (200.0, 150.0), 17.3, devices=[0])
+    many = _run(aai, src, 1.0, 0.37, (200.0, 150.0), 17.3, devices=list(range(n)) if n > 1 else [0, 0][:1])
+    assert np.array_equal(one.dst, many.dst)
+
+
+def test_argument_errors_are_reported_not_crashed(aai):
+    import torch
+
+    plan = aai.make_plan(64, 64, 1.0, 0.5, (32, 32), 10.0)
+    src = torch.zeros(64, 64, dtype=torch.float32, device="cuda")
+    bad = torch.zeros(5, 5, dtype=torch.float32, device="cuda")
+    with pytest.raises(aai.AaiError) as ei:
+        aai.run_device(plan, aai.tensor_image(src), aai.tensor_image(bad))
+    assert ei.value.status == aai.ERR_ARGUMENT
+    dst = torch.zeros(plan.dst_h, plan.dst_w, dtype=torch.float32, device="cuda")
+    with pytest.raises(aai.AaiError):
+        aai.run_device(plan, aai.tensor_image(src), aai.tensor_image(dst), mode=3)
+    # a source band that misses rows the canvas band needs is refused
+    with pytest.raises(aai.AaiError):
+        aai.run_device(plan, aai.tensor_image(src[:8].contiguous(), y0=0, height=64), aai.tensor_image(dst))
+
+
+# ---- properties (size independent) + full-size configurations -------------------------------------------------------
+
+def _device_run(aai, plan, src_t, out_dtype, arith=0, mode=1):
+    import torch
+
+    dst = torch.empty((plan.dst_h, plan.dst_w) + tuple(src_t.shape[2:]), dtype=out_dtype, device="cuda")
+    aai.run_device(plan, aai.tensor_image(src_t), aai.tensor_image(dst), mode=mode, arith=arith,
+                   stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return dst
+
+
+def test_constant_image_and_linearity(aai):
+    import torch
+
+    w, h, ratio, angle, iso = 1024, 768, 0.37, 17.3, (512.0, 384.0)
+    plan = aai.make_plan(w, h, 1.0, ratio, iso, angle)
+    const = torch.full((h, w), 1234.5, dtype=torch.float64, device="cuda")
+    out = _device_run(aai, plan, const, torch.float64)
+    covered = out != 0
+    assert 0.5 < covered.double().mean().item() < 0.75
+    assert (out[covered] - 1234.5).abs().max().item() <= 1e-9 * 1234.5  # weights normalise to 1
+    a = torch.rand(h, w, dtype=torch.float64, device="cuda")
+    b = torch.rand(h, w, dtype=torch.float64, device="cuda")
+    fa, fb = _device_run(aai, plan, a, torch.float64), _device_run(aai, plan, b, torch.float64)
+    fab = _device_run(aai, plan, 2.0 * a - 3.0 * b, torch.float64)
+    assert (fab - (2.0 * fa - 3.0 * fb)).abs().max().item() <= 1e-12
+
+
+def test_full_size_cfg4_sample_rows_and_properties(aai, oracle):
+    """BASELINE config 4: 16384^2 float32, 0.37x, 17.3 deg -> 7591^2.  Whole-image oracle would take ~40 min;
+    check sampled rows against the oracle plus the constant-image property on the full canvas."""
+    import torch
+
+    from area_average_interpolation_b200.synthetic import synthetic_image
+
+    W = 16384
+    plan = aai.make_plan(W, W, 1.0, 0.37, (8192.0, 8192.0), 17.3)
+    assert (plan.dst_w, plan.dst_h) == (7591, 7591)
+    src = synthetic_image(W, W, np.float32, 20201 + 4)
+    src_t = torch.from_numpy(src).cuda()
+    out = _device_run(aai, plan, src_t, torch.float64).cpu().numpy()
+    for row in (0, 1, 1700, 3795, 3796, 6000, 7589, 7590):
+        st, want, _ = oracle.run(src, 1.0, 0.37, (8192.0, 8192.0), 17.3, rows=(row, row + 1))
+        err = rel_err(out[row:row + 1], want)
+        assert err.max() <= TOL_F64_REL, (row, float(err.max()))
+    frac = (out != 0).mean()
+    assert 0.62 < frac < 0.65  # covered fraction 0.638
+    ones = _device_run(aai, plan, torch.ones(W, W, dtype=torch.float32, device="cuda"), torch.float64)
+    nz = ones != 0
+    assert (ones[nz] - 1.0).abs().max().item() <= 1e-12
+    assert nz.double().mean().item() == pytest.approx(frac, abs=1e-6)
+
+
+def test_full_size_cfg3_rgb_upscale_sample_rows(aai, oracle):
+    """BASELINE config 3 on a quarter-size source (2048^2 RGB u8, 1.7x, 45 deg, scale 3 -> 4924^2 canvas x3):
+    sampled rows against the oracle; the full 8192^2 case runs in bench.py --config 3."""
+    import torch
+
+    from area_average_interpolation_b200.synthetic import synthetic_image
+
+    W = 2048
+    iso = (W / 2 - 0.5, W / 2 - 0.5)
+    plan = aai.make_plan(W, W, 1.0, 1.7, iso, 45.0)
+    assert plan.scale == 3
+    src = synthetic_image(W, W, np.uint8, 20201 + 3, channels=3)
+    out = _device_run(aai, plan, torch.from_numpy(src).cuda(), torch.float32).cpu().numpy()
+    for row in (0, 2462, 4000, plan.dst_h - 1):
+        for c in (0, 2):
+            st, want, _ = oracle.run(src, 1.0, 1.7, iso, 45.0, rows=(row, row + 1), channel=c)
+            assert np.abs(out[row:row + 1, :, c] - want).max() <= TOL_U8_ABS, (row, c)
+
+
+def test_full_size_cfg5_slice_axis_aligned(aai, oracle):
+    """BASELINE config 5, one 4096^2 float32 slice, 0.5x axis-aligned: 2x2-box / (1/2,1,1/2) taps."""
+    import torch
+
+    from area_average_interpolation_b200.synthetic import synthetic_image
+
+    W = 4096
+    plan = aai.make_plan(W, W, 1.0, 0.5, (2048.0, 2048.0), 0.0)
+    assert plan.axis_aligned == 1 and (plan.dst_w, plan.dst_h) == (2048, 2048)
+    src = synthetic_image(W, W, np.float32, 20201 + 5)
+    out = _device_run(aai, plan, torch.from_numpy(src).cuda(), torch.float64).cpu().numpy()
+    for row in (0, 1, 1024, 2047):
+        st, want, _ = oracle.run(src, 1.0, 0.5, (2048.0, 2048.0), 0.0, rows=(row, row + 1))
+        assert rel_err(out[row:row + 1], want).max() <= TOL_F64_REL, row
+    # closed form for interior pixels: taps (1/2,1,1/2)^2 / 4 around source pixel (2x, 2y)
+    s = src.astype(np.float64)
+    y, x = 777, 1234
+    k = np.array([0.5, 1.0, 0.5])
+    want = (s[2 * y - 1:2 * y + 2, 2 * x - 1:2 * x + 2] * np.outer(k, k)).sum() / 4.0
+    assert abs(out[y, x] - want) <= 1e-9 * abs(want)

@@ -1,0 +1,123 @@
+"""CPU: host logic of the product (plan, partitioner) and the C-ABI surface.  No GPU compute here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from common import load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def aai(built):
+    import area_average_interpolation_b200 as m
+
+    return m
+
+
+def test_library_exports_every_declared_symbol(aai):
+    header = open(os.path.join(ROOT, "include", "aai.h")).read()
+    names = sorted(set(re.findall(r"\b(aai_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 14
+    lib = C.CDLL(aai.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/aai.h but not exported"
+
+
+def test_struct_layouts_match_the_header(aai):
+    # sizes implied by include/aai.h (4 x int32, 6 x int64, 14 x double) / (ptr, 5 x int64, 2 x int32)
+    assert C.sizeof(aai.Plan) == 4 * 4 + 6 * 8 + 14 * 8
+    assert C.sizeof(aai.Image) == 8 + 5 * 8 + 2 * 4
+
+
+def test_plan_matches_golden_sizes_and_isocentres(aai):
+    _, meta = load_golden()
+    for case in meta["cases"]:
+        p = aai.make_plan(case["w"], case["h"], case["src_res"], case["dst_res"], case["iso"], case["angle"])
+        assert p.status == 0
+        assert [p.dst_h, p.dst_w] == case["dst_shape"], case["name"]
+        assert [p.dst_iso_x, p.dst_iso_y] == case["dst_iso"], case["name"]
+
+
+def test_plan_validation_matches_reference_messages(aai):
+    _, meta = load_golden()
+    for e in meta["errors"]:
+        p = aai.make_plan(e["w"], e["h"], e["src_res"], e["dst_res"], (1.0, 1.0), 10.0)
+        assert 1 <= p.status <= 4
+        assert p.message == e["message"], e["name"]
+    # the operator mirror reports them like the reference: ok=False, message, dst untouched, dstIsocenter untouched
+    op = aai.AreaAverageInterpolation()
+    r = op.areaAverageInterpolation(np.ones((4, 4)), (1.0, 2.0), 1.0, (2, 2), 0.0, dstIsocenter=(-7.0, -9.0))
+    assert (r.ok, r.message, r.dst.size, r.dst_isocenter) == (False, "Assumed X & Y resolution are same.", 0, (-7.0, -9.0))
+    r = op.areaAverageInterpolation(np.ones((0, 0)), 1.0, 1.0, (2, 2), 0.0)
+    assert (r.ok, r.message) == (False, "There is no data in src array.")
+
+
+def test_plan_rejects_what_the_reference_cannot_handle(aai):
+    assert aai.make_plan(8, 8, 1.0, 1.0, (4, 4), float("nan")).status == aai.ERR_ANGLE
+    assert aai.make_plan(8, 8, 1.0, 1.0, (4, 4), float("inf")).status == aai.ERR_ANGLE
+    assert aai.make_plan(1 << 31, 8, 1.0, 1.0, (4, 4), 0.0).status == aai.ERR_ARGUMENT
+
+
+def test_plan_matches_oracle_plan_on_a_sweep(aai):
+    from oracle import port
+
+    rng = np.random.default_rng(0)
+    for _ in range(1500):
+        w, h = int(rng.integers(1, 300)), int(rng.integers(1, 300))
+        r = float(rng.choice([0.2, 0.37, 0.5, 0.9, 1.0, 1.7, 2.3, rng.uniform(0.05, 3)]))
+        ang = float(rng.choice([0, 90, 180, 270, 360, -90, 45, 30, 17.3, rng.uniform(-400, 800)]))
+        iso = (float(rng.uniform(-50, 350)), float(rng.uniform(-50, 350)))
+        p, o = aai.make_plan(w, h, 1.0, r, iso, ang), port.plan(w, h, 1.0, r, iso, ang)
+        assert (p.status, p.scale, p.quadrant, p.dst_w, p.dst_h, p.dst_iso_x, p.dst_iso_y, p.mod_w, p.mod_h, p.side,
+                p.sin_t, p.cos_t) == (o["status"], o["scale"], o["quadrant"], o["dstW"], o["dstH"], o["dstIsoX"],
+                                      o["dstIsoY"], o["modW"], o["modH"], o["side"], o["sn"], o["cs"])
+
+
+def test_axis_aligned_flag(aai):
+    for ang, flag in [(0, 1), (90, 1), (180, 1), (270, 1), (360, 1), (-90, 1), (45, 0), (1e-9, 0), (17.3, 0)]:
+        assert aai.make_plan(32, 32, 1.0, 0.5, (16, 16), ang).axis_aligned == flag, ang
+
+
+def test_partition_covers_canvas_and_balances_covered_pixels(aai):
+    p = aai.make_plan(16384, 16384, 1.0, 0.37, (8192, 8192), 17.3)
+    assert (p.dst_w, p.dst_h) == (7591, 7591)
+    total = aai.covered_pixels(p)
+    assert 0.60 * p.dst_w * p.dst_h < total < 0.68 * p.dst_w * p.dst_h  # covered fraction 0.638
+    for n in (1, 2, 4, 8):
+        b = aai.partition_rows(p, n)
+        assert b[0] == 0 and b[-1] == p.dst_h and all(b[i] < b[i + 1] for i in range(n))
+        loads = [aai.covered_pixels(p, b[i], b[i + 1]) for i in range(n)]
+        assert sum(loads) == total
+        assert max(loads) <= 1.05 * total / n, (n, loads)
+
+
+def test_band_source_window_contains_every_pixel_the_oracle_reads(aai):
+    # brute force on a small rotated case: the band's halo must contain all source pixels with non-zero weight
+    from oracle import port
+
+    w, h, r, ang, iso = 61, 47, 0.37, 117.3, (30.0, 20.0)
+    p = aai.make_plan(w, h, 1.0, r, iso, ang)
+    b = aai.partition_rows(p, 3)
+    base = np.zeros((h, w))
+    st, full, _ = port.run(np.ones((h, w)), 1.0, r, iso, ang)
+    for k in range(3):
+        x0, x1, y0, y1 = aai.band_source_window(p, b[k], b[k + 1])
+        assert 0 <= x0 <= x1 <= w and 0 <= y0 <= y1 <= h
+        # zero everything outside the halo: the band must not change
+        masked = base.copy()
+        masked[y0:y1, x0:x1] = 1.0
+        st, got, _ = port.run(masked, 1.0, r, iso, ang, rows=(b[k], b[k + 1]))
+        assert np.array_equal(got, full[b[k]:b[k + 1]]), k
+
+
+def test_no_cpu_fallback_without_a_gpu(aai):
+    if aai.device_count() > 0:
+        pytest.skip("a GPU is present")
+    op = aai.AreaAverageInterpolation()
+    with pytest.raises(aai.AaiError) as ei:
+        op.areaAverageInterpolation(np.ones((8, 8)), 1.0, 0.5, (4, 4), 0.0)
+    assert ei.value.status in (aai.ERR_NO_DEVICE, aai.ERR_CUDA)

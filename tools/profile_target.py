@@ -1,0 +1,39 @@
+"""Small target for ncu: the dominant kernel of one BASELINE config, device-resident, a few launches.
+    python tools/profile_target.py --config 4 --steps 3 [--arith f64|f32]
+(random device data instead of the seeded host generator: the profile does not depend on pixel values)."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import area_average_interpolation_b200 as aai
+from bench import CONFIGS
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", type=int, default=4)
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--arith", default="f64")
+args = ap.parse_args()
+cfg = CONFIGS[args.config]
+dev = torch.device("cuda:0")
+plan = aai.make_plan(cfg["w"], cfg["h"], 1.0, cfg["ratio"], cfg["iso"], cfg["angle"])
+tail = (cfg["ch"],) if cfg["ch"] > 1 else ()
+if cfg["dtype"] == "uint8":
+    src = torch.randint(0, 256, (cfg["h"], cfg["w"]) + tail, dtype=torch.uint8, device=dev)
+else:
+    src = torch.rand((cfg["h"], cfg["w"]) + tail, dtype=torch.float32, device=dev) * 4096
+dst = torch.empty((plan.dst_h, plan.dst_w) + tail, dtype=torch.float32, device=dev)
+si, di = aai.tensor_image(src), aai.tensor_image(dst)
+arith = aai.ARITH_F32 if args.arith == "f32" else aai.ARITH_F64
+st = torch.cuda.current_stream().cuda_stream
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+aai.run_device(plan, si, di, arith=arith, stream=st)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(args.steps):
+    aai.run_device(plan, si, di, arith=arith, stream=st)
+e1.record()
+torch.cuda.synchronize()
+print(f"{cfg['label']}: canvas {plan.dst_w}x{plan.dst_h}, {e0.elapsed_time(e1) / args.steps:.3f} ms per launch")
