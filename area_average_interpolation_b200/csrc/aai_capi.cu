@@ -121,6 +121,23 @@ AaiKernelParams aai_make_kernel_params(const aai_plan &p, const aai_image &src, 
     g.inv_s = 1.0 / s;
     g.m = (c + s) / 2;
     g.thr = std::fabs(c - s) / 2;
+    AaiShapeF &f = k.shapef;
+    f.cs = (float)c;
+    f.sn = (float)s;
+    f.half = (float)h;
+    f.k_sc = (float)g.k_sc;
+    f.k_hc = (float)g.k_hc;
+    f.k_cs = (float)g.k_cs;
+    f.k_hs = (float)g.k_hs;
+    f.inv_c = (float)g.inv_c;
+    f.inv_s = (float)g.inv_s;
+    f.m = (float)g.m;
+    f.thr = (float)g.thr;
+    // guard band of the FP32 shape decisions: ~8x the rounding error of the FP32 margins, which scales with 1/sin,
+    // 1/cos; near-axis angles (1/sin or 1/cos > 20) use the FP64 kernel
+    const double amp = std::fmax(1.0, std::fmax(g.inv_c, g.inv_s));
+    f.tau = (float)(4e-6 * amp);
+    k.f32_ok = (s > 0.0 && c > 0.0 && amp <= 20.0) ? 1 : 0;
     k.reach = p.reach;
     k.hb = h * (c + s);
     k.mod_w = (int32_t)p.mod_w;

@@ -100,4 +100,90 @@ AAI_HD double aai_pair_area(const AaiShape &g, double cx, double cy, int i, int 
                          aai_overlap1(ytL, ybL, ry), aai_overlap1(ytR, ybR, ry));
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// FP32 variant ("FP32 kernel" of the north star): coordinates are taken relative to the footprint centre in FP64
+// and rounded once; lengths, areas and sums are FP32; the shape decision of the quirk is made in FP32 with a
+// guard band: when any decisive margin is within `tau` of zero the caller must redo the pixel in FP64
+// (`uncertain` is set), so that no FP32 rounding can flip a discontinuous decision.
+// ------------------------------------------------------------------------------------------------------------
+struct AaiShapeF {
+    float cs, sn, half;
+    float k_sc, k_hc, k_cs, k_hs;
+    float inv_c, inv_s;
+    float m, thr;
+    float tau;  // guard band of the FP32 decisions (distance / edge-parameter units)
+};
+
+AAI_HD float aai_sat(float x) {
+#if defined(__CUDA_ARCH__)
+    return __saturatef(x);
+#else
+    return fminf(fmaxf(x, 0.0f), 1.0f);
+#endif
+}
+// length of [lo, hi] ∩ [e, e+1] for hi >= lo, without min/max (maps to FADD.SAT)
+AAI_HD float aai_overlap1_f32(float lo, float hi, float e) { return aai_sat(hi - e) - aai_sat(lo - e); }
+
+AAI_HD void aai_chord_h_f32(const AaiShapeF &g, float ty, float &xl, float &xr) {
+    xl = fmaxf(fmaf(ty, g.k_sc, -g.k_hc), fmaf(-ty, g.k_cs, -g.k_hs));
+    xr = fminf(fmaf(ty, g.k_sc, g.k_hc), fmaf(-ty, g.k_cs, g.k_hs));
+    xr = fmaxf(xr, xl);  // empty chord -> zero length
+}
+AAI_HD void aai_chord_v_f32(const AaiShapeF &g, float tx, float &yt, float &yb) {
+    yt = fmaxf(fmaf(tx, g.k_cs, -g.k_hs), fmaf(-tx, g.k_sc, -g.k_hc));
+    yb = fminf(fmaf(tx, g.k_cs, g.k_hs), fmaf(-tx, g.k_sc, g.k_hc));
+    yb = fmaxf(yb, yt);
+}
+
+// (u0, v0): footprint-local coordinates of the cell centre.  Sets `uncertain` (never clears it).
+AAI_HD float aai_cell_area_f32(const AaiShapeF &g, float u0, float v0, float lenT, float lenB, float lenL,
+                               float lenR, bool &uncertain) {
+    const float ca = copysignf(g.half, u0) - u0;  // V - cell centre, along u
+    const float cb = copysignf(g.half, v0) - v0;  // V - cell centre, along v
+    const float vx = fmaf(ca, g.cs, cb * g.sn);
+    const float vy = fmaf(cb, g.cs, -ca * g.sn);
+    float area = fmaf(0.25f, (lenT + lenB) + (lenL + lenR), 0.5f * fmaf(vy, lenT - lenB, vx * (lenL - lenR)));
+    const float a = g.half - fabsf(u0);
+    const float aa = fabsf(a);
+    if (aa > g.thr - g.tau && aa < g.m + g.tau) {
+        const float sv = copysignf(1.0f, v0), su = copysignf(1.0f, u0);
+        const float wx = sv * vx, wy = sv * vy;
+        const float u_in = fmaxf((wx - 0.5f) * g.inv_s, (wy - 0.5f) * g.inv_c);
+        const float u_out = fminf((wx + 0.5f) * g.inv_s, (wy + 0.5f) * g.inv_c);
+        const float zx = su * vx, zy = su * vy;
+        const float v_in = fmaxf((zx - 0.5f) * g.inv_c, (-0.5f - zy) * g.inv_s);
+        const float v_out = fminf((zx + 0.5f) * g.inv_c, (0.5f - zy) * g.inv_s);
+        // fire  <=>  min(aa-thr, m-aa, u_in, u_out-u_in) > 0  and  min(v_out-v_in, v_out) <= 0
+        const float need = fminf(fminf(aa - g.thr, g.m - aa), fminf(u_in, u_out - u_in));
+        const float veto = fminf(v_out - v_in, v_out);
+        const bool fire_hi = need > -g.tau && veto <= g.tau;   // decision if every doubtful margin helps
+        const bool fire_lo = need > g.tau && veto <= -g.tau;   // decision if every doubtful margin hurts
+        if (fire_hi && !fire_lo) uncertain = true;
+        if (need > 0.0f && veto <= 0.0f) {
+            if (a < 0.0f) {
+                const float d = a + g.m;
+                area = 0.5f * (1.0f - d * g.inv_c) * (1.0f - d * g.inv_s);
+            } else {
+                const float d = a - g.m;
+                area = 1.0f - 0.5f * (1.0f + d * g.inv_c) * (1.0f + d * g.inv_s);
+            }
+        }
+    }
+    return area;
+}
+
+// Stand-alone FP32 form for one pair (tests): (fx, fy) = footprint centre minus the nearest integer lattice point,
+// (di, dj) = cell index relative to that lattice point.
+AAI_HD float aai_pair_area_f32(const AaiShapeF &g, float fx, float fy, int di, int dj, bool &uncertain) {
+    const float rx = (float)di - fx, ry = (float)dj - fy;
+    float xlT, xrT, xlB, xrB, ytL, ybL, ytR, ybR;
+    aai_chord_h_f32(g, ry - 0.5f, xlT, xrT);
+    aai_chord_h_f32(g, ry + 0.5f, xlB, xrB);
+    aai_chord_v_f32(g, rx - 0.5f, ytL, ybL);
+    aai_chord_v_f32(g, rx + 0.5f, ytR, ybR);
+    const float u0 = fmaf(rx, g.cs, -ry * g.sn), v0 = fmaf(rx, g.sn, ry * g.cs);
+    return aai_cell_area_f32(g, u0, v0, aai_overlap1_f32(xlT, xrT, rx - 0.5f), aai_overlap1_f32(xlB, xrB, rx - 0.5f),
+                             aai_overlap1_f32(ytL, ybL, ry - 0.5f), aai_overlap1_f32(ytR, ybR, ry - 0.5f), uncertain);
+}
+
 #endif  // AAI_CELL_CUH_

@@ -13,6 +13,8 @@ struct AaiKernelParams {
     // canvas-pixel centre expression of Source.cpp:212-219
     double side, off_ix, off_iy, iso_x, iso_y, off_x, off_y;
     AaiShape shape;   // cos/sin, h = L/2 and the derived footprint constants (aai_cell.cuh)
+    AaiShapeF shapef; // the same in FP32 (+ guard band) for the FP32 kernel
+    int32_t f32_ok;   // FP32 kernel admissible (angle not within ~3 degrees of an axis)
     double reach;     // L*sqrt(2)/2 (search window, 426-429)
     double hb;        // h*(c+s): half extent of the footprint's axis-aligned bounding box
     int32_t mod_w, mod_h, dst_w, dst_h;

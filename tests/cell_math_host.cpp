@@ -43,3 +43,26 @@ extern "C" void aai_test_image_f64(double c, double s, double L, double offIx, d
             out[(size_t)y * dstW + x] = 2.220446049250313e-16 < std::fabs(sumA) ? acc / sumA : 0.0;
         }
 }
+
+static AaiShapeF make_shape_f(double c, double s, double L) {
+    AaiShapeF g;
+    const double h = L / 2;
+    g.cs = (float)c; g.sn = (float)s; g.half = (float)h;
+    g.k_sc = (float)(s / c); g.k_hc = (float)(h / c); g.k_cs = (float)(c / s); g.k_hs = (float)(h / s);
+    g.inv_c = (float)(1.0 / c); g.inv_s = (float)(1.0 / s);
+    g.m = (float)((c + s) / 2); g.thr = (float)(std::fabs(c - s) / 2);
+    g.tau = (float)(4e-6 * std::fmax(1.0, std::fmax(1.0 / c, 1.0 / s)));
+    return g;
+}
+
+// FP32 pair areas + the "uncertain" flag (1 = the kernel would redo this pixel in FP64)
+extern "C" void aai_test_pair_areas_f32(double c, double s, double L, const double *cx, const double *cy, const int *i,
+                                        const int *j, float *out, unsigned char *flag, long long n) {
+    const AaiShapeF g = make_shape_f(c, s, L);
+    for (long long k = 0; k < n; ++k) {
+        const double ix = std::nearbyint(cx[k]), iy = std::nearbyint(cy[k]);
+        bool unc = false;
+        out[k] = aai_pair_area_f32(g, (float)(cx[k] - ix), (float)(cy[k] - iy), i[k] - (int)ix, j[k] - (int)iy, unc);
+        flag[k] = unc ? 1 : 0;
+    }
+}
