@@ -137,7 +137,8 @@ AaiKernelParams aai_make_kernel_params(const aai_plan &p, const aai_image &src, 
     // 1/cos; near-axis angles (1/sin or 1/cos > 20) use the FP64 kernel
     const double amp = std::fmax(1.0, std::fmax(g.inv_c, g.inv_s));
     f.tau = (float)(4e-6 * amp);
-    k.f32_ok = (s > 0.0 && c > 0.0 && amp <= 20.0) ? 1 : 0;
+    const uint64_t max_e = (uint64_t)(p.mod_w > p.mod_h ? p.mod_w : p.mod_h);
+    k.f32_ok = (s > 0.0 && c > 0.0 && amp <= 20.0 && max_e * p.scale < 0x100000000ULL) ? 1 : 0;
     k.reach = p.reach;
     k.hb = h * (c + s);
     k.mod_w = (int32_t)p.mod_w;
@@ -146,6 +147,14 @@ AaiKernelParams aai_make_kernel_params(const aai_plan &p, const aai_image &src, 
     k.dst_h = (int32_t)p.dst_h;
     k.scale = (int32_t)p.scale;
     k.quadrant = p.quadrant;
+    const int32_t mw1 = (int32_t)p.mod_w - 1, mh1 = (int32_t)p.mod_h - 1;
+    switch (p.quadrant) {
+        case 0: k.e_axi = 1; k.e_axj = 0; k.e_ax0 = 0; k.e_ayi = 0; k.e_ayj = 1; k.e_ay0 = 0; break;
+        case 1: k.e_axi = 0; k.e_axj = 1; k.e_ax0 = 0; k.e_ayi = -1; k.e_ayj = 0; k.e_ay0 = mw1; break;
+        case 2: k.e_axi = -1; k.e_axj = 0; k.e_ax0 = mw1; k.e_ayi = 0; k.e_ayj = -1; k.e_ay0 = mh1; break;
+        default: k.e_axi = 0; k.e_axj = -1; k.e_ax0 = mh1; k.e_ayi = 1; k.e_ayj = 0; k.e_ay0 = 0; break;
+    }
+    k.div_magic = p.scale > 1 ? (uint32_t)(0x100000000ULL / p.scale) + 1u : 0u;
     k.src = src.data;
     k.src_pitch = src.pitch_bytes;
     k.src_w = (int32_t)src.width;

@@ -114,6 +114,14 @@ struct AaiShapeF {
     float tau;  // guard band of the FP32 decisions (distance / edge-parameter units)
 };
 
+AAI_HD bool aai_sign_product_positive(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    return (__float_as_int(a) ^ __float_as_int(b) ^ __float_as_int(c)) >= 0;
+#else
+    return ((signbit(a) ? 1 : 0) ^ (signbit(b) ? 1 : 0) ^ (signbit(c) ? 1 : 0)) == 0;
+#endif
+}
+
 AAI_HD float aai_sat(float x) {
 #if defined(__CUDA_ARCH__)
     return __saturatef(x);
@@ -135,46 +143,43 @@ AAI_HD void aai_chord_v_f32(const AaiShapeF &g, float tx, float &yt, float &yb) 
     yb = fmaxf(yb, yt);
 }
 
-// (u0, v0): footprint-local coordinates of the cell centre.  Sets `uncertain` (never clears it).
+// (u0, v0): footprint-local coordinates of the cell centre.  `worst` accumulates the smallest |margin| of the
+// quirk decision over the cells of a pixel: the caller redoes the pixel in FP64 when worst < g.tau.
+//
+// Quirk decision, branch-free (derivation in DESIGN.md §3.3).  Work in the frame W = sv * (cell-local), where the
+// nearest left/right edge is the ray from W = sv*V along -(s,c) and the nearest top/bottom edge the ray from W along
+// rho*(-c,s), rho = su*sv.  The edge line isolates exactly one corner iff thr < |a| < m; that corner is the
+// top-right one (lambda = rho*sign(a) > 0) or the bottom-left one (lambda < 0).  With (p,q,kk) = (wx,wy,s/c) resp.
+// (wy,wx,c/s):  both crossings lie on the edge SEGMENT iff p > 1/2 and q > -1/2, and the top/bottom edge misses the
+// cell iff a < 0 (it runs away from the cell) or q + kk (p - 1/2) > 1/2.
 AAI_HD float aai_cell_area_f32(const AaiShapeF &g, float u0, float v0, float lenT, float lenB, float lenL,
-                               float lenR, bool &uncertain) {
+                               float lenR, float &worst) {
     const float ca = copysignf(g.half, u0) - u0;  // V - cell centre, along u
     const float cb = copysignf(g.half, v0) - v0;  // V - cell centre, along v
     const float vx = fmaf(ca, g.cs, cb * g.sn);
     const float vy = fmaf(cb, g.cs, -ca * g.sn);
-    float area = fmaf(0.25f, (lenT + lenB) + (lenL + lenR), 0.5f * fmaf(vy, lenT - lenB, vx * (lenL - lenR)));
+    const float area = fmaf(0.25f, (lenT + lenB) + (lenL + lenR), 0.5f * fmaf(vy, lenT - lenB, vx * (lenL - lenR)));
     const float a = g.half - fabsf(u0);
     const float aa = fabsf(a);
-    if (aa > g.thr - g.tau && aa < g.m + g.tau) {
-        const float sv = copysignf(1.0f, v0), su = copysignf(1.0f, u0);
-        const float wx = sv * vx, wy = sv * vy;
-        const float u_in = fmaxf((wx - 0.5f) * g.inv_s, (wy - 0.5f) * g.inv_c);
-        const float u_out = fminf((wx + 0.5f) * g.inv_s, (wy + 0.5f) * g.inv_c);
-        const float zx = su * vx, zy = su * vy;
-        const float v_in = fmaxf((zx - 0.5f) * g.inv_c, (-0.5f - zy) * g.inv_s);
-        const float v_out = fminf((zx + 0.5f) * g.inv_c, (0.5f - zy) * g.inv_s);
-        // fire  <=>  min(aa-thr, m-aa, u_in, u_out-u_in) > 0  and  min(v_out-v_in, v_out) <= 0
-        const float need = fminf(fminf(aa - g.thr, g.m - aa), fminf(u_in, u_out - u_in));
-        const float veto = fminf(v_out - v_in, v_out);
-        const bool fire_hi = need > -g.tau && veto <= g.tau;   // decision if every doubtful margin helps
-        const bool fire_lo = need > g.tau && veto <= -g.tau;   // decision if every doubtful margin hurts
-        if (fire_hi && !fire_lo) uncertain = true;
-        if (need > 0.0f && veto <= 0.0f) {
-            if (a < 0.0f) {
-                const float d = a + g.m;
-                area = 0.5f * (1.0f - d * g.inv_c) * (1.0f - d * g.inv_s);
-            } else {
-                const float d = a - g.m;
-                area = 1.0f - 0.5f * (1.0f + d * g.inv_c) * (1.0f + d * g.inv_s);
-            }
-        }
-    }
-    return area;
+    const float wx = copysignf(1.0f, v0) * vx, wy = copysignf(1.0f, v0) * vy;
+    // lambda = su*sv*sign(a) > 0: the isolated corner is the top-right one (W frame).  Taken from the SIGN BITS so
+    // that it stays consistent with copysign() above when u0 or v0 is exactly +-0 (symmetric configurations).
+    const bool tr = aai_sign_product_positive(u0, v0, a);
+    const float p = tr ? wx : wy, q = tr ? wy : wx, kk = tr ? g.k_sc : g.k_cs;
+    const float m2 = g.m - aa;
+    const float m3 = p - 0.5f;
+    const float m5 = a < 0.0f ? 1.0f : fmaf(kk, m3, q - 0.5f);
+    const float need = fminf(fminf(fminf(aa - g.thr, m2), fminf(m3, q + 0.5f)), m5);
+    worst = fminf(worst, fabsf(need));
+    // reference shape 2 (one corner inside, a < 0) / shape 4 (one corner outside): legs 1 - t/c and 1 - t/s
+    const float tri = 0.5f * fmaf(-m2, g.inv_c, 1.0f) * fmaf(-m2, g.inv_s, 1.0f);
+    const float quirk = a < 0.0f ? tri : 1.0f - tri;
+    return need > 0.0f ? quirk : area;
 }
 
 // Stand-alone FP32 form for one pair (tests): (fx, fy) = footprint centre minus the nearest integer lattice point,
 // (di, dj) = cell index relative to that lattice point.
-AAI_HD float aai_pair_area_f32(const AaiShapeF &g, float fx, float fy, int di, int dj, bool &uncertain) {
+AAI_HD float aai_pair_area_f32(const AaiShapeF &g, float fx, float fy, int di, int dj, float &worst) {
     const float rx = (float)di - fx, ry = (float)dj - fy;
     float xlT, xrT, xlB, xrB, ytL, ybL, ytR, ybR;
     aai_chord_h_f32(g, ry - 0.5f, xlT, xrT);
@@ -183,7 +188,7 @@ AAI_HD float aai_pair_area_f32(const AaiShapeF &g, float fx, float fy, int di, i
     aai_chord_v_f32(g, rx + 0.5f, ytR, ybR);
     const float u0 = fmaf(rx, g.cs, -ry * g.sn), v0 = fmaf(rx, g.sn, ry * g.cs);
     return aai_cell_area_f32(g, u0, v0, aai_overlap1_f32(xlT, xrT, rx - 0.5f), aai_overlap1_f32(xlB, xrB, rx - 0.5f),
-                             aai_overlap1_f32(ytL, ybL, ry - 0.5f), aai_overlap1_f32(ytR, ybR, ry - 0.5f), uncertain);
+                             aai_overlap1_f32(ytL, ybL, ry - 0.5f), aai_overlap1_f32(ytR, ybR, ry - 0.5f), worst);
 }
 
 #endif  // AAI_CELL_CUH_

@@ -1,0 +1,153 @@
+// Device helpers shared by the kernel translation units (aai_kernels.cu, aai_kernels_f32.cu).
+#ifndef AAI_DEVICE_CUH_
+#define AAI_DEVICE_CUH_
+
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdint>
+
+#include "aai_cell.cuh"
+#include "aai_internal.h"
+
+namespace aai_dev {
+
+constexpr int TILE_W = 16;
+constexpr int TILE_H = 16;
+
+template <typename T>
+struct SrcLoad;
+template <>
+struct SrcLoad<double> {
+    static __device__ __forceinline__ double get(const void *row, int idx) { return __ldg((const double *)row + idx); }
+};
+template <>
+struct SrcLoad<float> {
+    static __device__ __forceinline__ double get(const void *row, int idx) {
+        return (double)__ldg((const float *)row + idx);
+    }
+};
+template <>
+struct SrcLoad<uint8_t> {
+    static __device__ __forceinline__ double get(const void *row, int idx) {
+        return (double)__ldg((const uint8_t *)row + idx);
+    }
+};
+
+template <typename T>
+__device__ __forceinline__ void store_dst(void *row, int idx, double v);
+template <>
+__device__ __forceinline__ void store_dst<double>(void *row, int idx, double v) {
+    ((double *)row)[idx] = v;
+}
+template <>
+__device__ __forceinline__ void store_dst<float>(void *row, int idx, double v) {
+    ((float *)row)[idx] = (float)v;
+}
+template <>
+__device__ __forceinline__ void store_dst<uint8_t>(void *row, int idx, double v) {
+    // the reference defines no 8-bit store; documented rule: round half up, saturate to [0,255]
+    double r = floor(v + 0.5);
+    r = fmin(fmax(r, 0.0), 255.0);
+    ((uint8_t *)row)[idx] = (uint8_t)(int)r;
+}
+
+// expanded + quadrant-rotated pixel (mx,my) -> original source pixel (inverse of Source.cpp:163-168)
+__device__ __forceinline__ void mod_to_src(const AaiKernelParams &kp, int mx, int my, int &sx, int &sy) {
+    int ex, ey;
+    switch (kp.quadrant) {
+        case 0: ex = mx; ey = my; break;
+        case 1: ex = my; ey = kp.mod_w - 1 - mx; break;
+        case 2: ex = kp.mod_w - 1 - mx; ey = kp.mod_h - 1 - my; break;
+        default: ex = kp.mod_h - 1 - my; ey = mx; break;
+    }
+    if (kp.scale == 1) {
+        sx = ex;
+        sy = ey;
+    } else {
+        sx = ex / kp.scale;
+        sy = ey / kp.scale;
+    }
+}
+
+// canvas pixel centre, evaluated with the reference's operand order and no FMA contraction (212-219)
+__device__ __forceinline__ void pixel_centre(const AaiKernelParams &kp, int x, int y, double &cx, double &cy) {
+    const double u = __dadd_rn(__dsub_rn(__dmul_rn(__dadd_rn((double)x, kp.off_ix), kp.side), kp.iso_x), kp.off_x);
+    const double v = __dadd_rn(__dsub_rn(__dmul_rn(__dadd_rn((double)y, kp.off_iy), kp.side), kp.iso_y), kp.off_y);
+    cx = __dadd_rn(__dadd_rn(__dmul_rn(u, kp.shape.cs), __dmul_rn(v, kp.shape.sn)), kp.iso_x);
+    cy = __dadd_rn(__dadd_rn(__dmul_rn(-u, kp.shape.sn), __dmul_rn(v, kp.shape.cs)), kp.iso_y);
+}
+
+// the reference's clamped search window (426-429)
+__device__ __forceinline__ void search_window(const AaiKernelParams &kp, double cx, double cy, int &x0, int &x1,
+                                              int &y0, int &y1) {
+    x0 = max(0, __double2int_rd(__dsub_rn(__dsub_rn(cx, kp.reach), 1.0)));
+    x1 = min(__double2int_ru(__dadd_rn(__dadd_rn(cx, kp.reach), 1.0)), kp.mod_w - 1);
+    y0 = max(0, __double2int_rd(__dsub_rn(__dsub_rn(cy, kp.reach), 1.0)));
+    y1 = min(__double2int_ru(__dadd_rn(__dadd_rn(cy, kp.reach), 1.0)), kp.mod_h - 1);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FP64 evaluation of one canvas pixel over the cells [ix0,ix1] x [jy0,jy1] (also the precision fallback of the
+// FP32 kernel).
+// ------------------------------------------------------------------------------------------------------------
+template <typename TI, int NC>
+__device__ __forceinline__ void pixel_f64(const AaiKernelParams &kp, double cx, double cy, int ix0, int ix1, int jy0,
+                                          int jy1, double &sumA, double (&acc)[NC]) {
+    sumA = 0.0;
+#pragma unroll
+    for (int ch = 0; ch < NC; ++ch) acc[ch] = 0.0;
+    if (ix0 > ix1 || jy0 > jy1) return;
+    const AaiShape &g = kp.shape;
+    // chord of the footprint on the horizontal grid line through the top of row jy0 (relative to C)
+    double xlT, xrT;
+    aai_chord_h(g, ((double)jy0 - 0.5) - cy, xlT, xrT);
+    for (int j = jy0; j <= jy1; ++j) {
+        const double ry = (double)j - cy;
+        double xlB, xrB;
+        aai_chord_h(g, ry + 0.5, xlB, xrB);
+        // chord on the vertical grid line through the left of column ix0
+        double yt, yb;
+        aai_chord_v(g, ((double)ix0 - 0.5) - cx, yt, yb);
+        double lenL = aai_overlap1(yt, yb, ry);
+        for (int i = ix0; i <= ix1; ++i) {
+            const double rx = (double)i - cx;
+            aai_chord_v(g, rx + 0.5, yt, yb);
+            const double lenR = aai_overlap1(yt, yb, ry);
+            const double lenT = aai_overlap1(xlT, xrT, rx);
+            const double lenB = aai_overlap1(xlB, xrB, rx);
+            const double area = aai_cell_area(g, rx, ry, lenT, lenB, lenL, lenR);
+            lenL = lenR;
+            if (area != 0.0) {
+                int sx, sy;
+                mod_to_src(kp, i, j, sx, sy);
+                const char *row = (const char *)kp.src + (int64_t)(sy - kp.src_y0) * kp.src_pitch;
+                sumA += area;
+#pragma unroll
+                for (int ch = 0; ch < NC; ++ch) acc[ch] += SrcLoad<TI>::get(row, sx * NC + ch) * area;
+            }
+        }
+        xlT = xlB;
+        xrT = xrB;
+    }
+}
+
+// cells that can have non-zero overlap: |i - cx| < hb + 1/2, intersected with the reference's clamped window.
+// Returns true when the image border cut the range (a border pixel: some of its footprint lies outside the image).
+__device__ __forceinline__ bool cell_range(const AaiKernelParams &kp, double cx, double cy, int &ix0, int &ix1,
+                                           int &jy0, int &jy1) {
+    int wx0, wx1, wy0, wy1;
+    search_window(kp, cx, cy, wx0, wx1, wy0, wy1);
+    const double ext = kp.hb + 0.5 + 1e-9;
+    const int bx0 = __double2int_ru(cx - ext), bx1 = __double2int_rd(cx + ext);
+    const int by0 = __double2int_ru(cy - ext), by1 = __double2int_rd(cy + ext);
+    ix0 = max(wx0, bx0);
+    ix1 = min(wx1, bx1);
+    jy0 = max(wy0, by0);
+    jy1 = min(wy1, by1);
+    return bx0 < 0 || by0 < 0 || bx1 > kp.mod_w - 1 || by1 > kp.mod_h - 1;
+}
+
+}  // namespace aai_dev
+
+#endif  // AAI_DEVICE_CUH_

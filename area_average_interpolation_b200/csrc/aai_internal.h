@@ -19,6 +19,10 @@ struct AaiKernelParams {
     double hb;        // h*(c+s): half extent of the footprint's axis-aligned bounding box
     int32_t mod_w, mod_h, dst_w, dst_h;
     int32_t scale, quadrant;
+    // expanded + quadrant-rotated pixel (i,j) -> expanded pixel (ex,ey) = (axi*i + axj*j + ax0, ayi*i + ayj*j + ay0)
+    // (inverse of Source.cpp:163-168), then source pixel = (ex/scale, ey/scale) via a multiply-high
+    int32_t e_axi, e_axj, e_ax0, e_ayi, e_ayj, e_ay0;
+    uint32_t div_magic;  // floor(2^32/scale)+1: exact for ex*scale < 2^32
     // source view (original frame): rows [src_y0, src_y0+src_rows) are present
     const void *src;
     int64_t src_pitch;
@@ -37,6 +41,11 @@ AaiKernelParams aai_make_kernel_params(const aai_plan &plan, const aai_image &sr
 int aai_launch_overlap(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_separable(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_fast(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
+// aai_kernels_f32.cu, one translation unit per maximum cell count per axis
+int aai_launch_overlap_f32_n4(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
+int aai_launch_overlap_f32_n5(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
+int aai_launch_overlap_f32_n6(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
+int aai_launch_overlap_f32_n8(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
 
 void aai_set_error(const char *fmt, ...);
 

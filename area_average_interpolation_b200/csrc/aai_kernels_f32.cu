@@ -1,0 +1,199 @@
+// Overlap kernel, FP32 arithmetic (the north star's "FP32 kernel") -- main loop of
+// AreaAverageInterpolation::areaAverageInterpolation (Source.cpp:411-579) for float / 8-bit images.
+//
+// Compiled once per AAI_MAXN (4, 5, 6, 8 = maximum number of source cells per axis that one footprint can
+// touch; the host picks the smallest that fits L(cos+sin)+1), so that the column loop is fully unrolled and the
+// MAXN+1 vertical-line chords of the footprint live in registers.
+//
+// Same formulation as the FP64 kernel (aai_kernels.cu), on footprint-local coordinates:
+//   * the footprint centre is computed in FP64 exactly like the reference (212-219) and split into the nearest
+//     lattice point + an FP32 fraction, so every FP32 quantity is O(L) with ~1e-7 absolute error;
+//   * side lengths |side ∩ footprint| are differences of FADD.SAT (no min/max on the half-rate ALU pipe);
+//   * the reference's shape-2/4 quirk is decided branch-free (aai_cell.cuh); the smallest decision margin of the
+//     pixel is tracked and, when it falls inside the FP32 guard band, or when the pixel's total overlap is tiny
+//     (border slivers need relative accuracy), the pixel is redone in FP64 (pixel_f64) -- FP32 rounding can never
+//     flip one of the reference's discontinuous decisions.
+#include "aai_device.cuh"
+
+#ifndef AAI_MAXN
+#error "compile with -DAAI_MAXN=4|5|6|8"
+#endif
+
+using namespace aai_dev;
+
+namespace {
+
+constexpr int MAXN = AAI_MAXN;
+
+template <typename T>
+struct LoadF;
+template <>
+struct LoadF<double> {
+    static __device__ __forceinline__ float get(const char *p) { return (float)__ldg((const double *)p); }
+};
+template <>
+struct LoadF<float> {
+    static __device__ __forceinline__ float get(const char *p) { return __ldg((const float *)p); }
+};
+template <>
+struct LoadF<uint8_t> {
+    static __device__ __forceinline__ float get(const char *p) { return (float)__ldg((const uint8_t *)p); }
+};
+
+template <typename T>
+__device__ __forceinline__ void store_f(void *row, int idx, float v);
+template <>
+__device__ __forceinline__ void store_f<double>(void *row, int idx, float v) {
+    ((double *)row)[idx] = (double)v;
+}
+template <>
+__device__ __forceinline__ void store_f<float>(void *row, int idx, float v) {
+    ((float *)row)[idx] = v;
+}
+template <>
+__device__ __forceinline__ void store_f<uint8_t>(void *row, int idx, float v) {
+    ((uint8_t *)row)[idx] = (uint8_t)__float2int_rd(fminf(fmaxf(v + 0.5f, 0.0f), 255.0f));  // round half up, saturate
+}
+
+// IDENT: scale 1, quadrant 0 (expanded pixel (i,j) IS source pixel (i,j)): constant element stride, offsets fold
+// into the load instruction.  Otherwise the general expanded-frame affine map + division by the scale.
+template <typename TI, typename TO, int NC, bool IDENT>
+__global__ void __launch_bounds__(TILE_W *TILE_H)
+    overlap_kernel_f32(const __grid_constant__ AaiKernelParams kp) {
+    const int x = blockIdx.x * TILE_W + threadIdx.x;
+    const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
+    if (x >= kp.dst_w || y >= kp.row1) return;
+    double cx, cy;
+    pixel_centre(kp, x, y, cx, cy);
+    int ix0, ix1, jy0, jy1;
+    const bool border = cell_range(kp, cx, cy, ix0, ix1, jy0, jy1);
+    const int ncols = ix1 - ix0 + 1, nrows = jy1 - jy0 + 1;
+    char *drow = (char *)kp.dst + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
+    if (ncols <= 0 || nrows <= 0) {  // footprint bounding box misses the image: the reference writes 0 (577)
+#pragma unroll
+        for (int ch = 0; ch < NC; ++ch) store_f<TO>(drow, x * NC + ch, 0.0f);
+        return;
+    }
+    float sumA = 0.0f, acc[NC];
+#pragma unroll
+    for (int ch = 0; ch < NC; ++ch) acc[ch] = 0.0f;
+    float worst = 1.0f;
+    // Border pixels (footprint partly outside the image) are normalised by a partial, possibly tiny, total area:
+    // they need relative accuracy, so they take the FP64 path (~0.1% of a large canvas).
+    bool redo = border || ncols > MAXN || nrows > MAXN;  // (the MAXN test cannot fire for the MAXN the host picked)
+    if (!redo) {
+        const AaiShapeF &g = kp.shapef;
+        const double rcx = rint(cx), rcy = rint(cy);
+        const float fx = (float)(cx - rcx), fy = (float)(cy - rcy);
+        const int dj0 = jy0 - (int)rcy;
+        const float rx0 = (float)(ix0 - (int)rcx) - fx;
+        float yt[MAXN + 1], yb[MAXN + 1];
+#pragma unroll
+        for (int k = 0; k <= MAXN; ++k) aai_chord_v_f32(g, rx0 + ((float)k - 0.5f), yt[k], yb[k]);
+        float xlT, xrT;
+        aai_chord_h_f32(g, ((float)dj0 - fy) - 0.5f, xlT, xrT);
+        constexpr int ESZ = (int)sizeof(TI) * NC;
+#pragma unroll 1
+        for (int r = 0; r < nrows; ++r) {
+            const float ry = (float)(dj0 + r) - fy;
+            float xlB, xrB;
+            aai_chord_h_f32(g, ry + 0.5f, xlB, xrB);
+            const float ey = ry - 0.5f;
+            float lenL = aai_overlap1_f32(yt[0], yb[0], ey);
+            const float ur = -ry * g.sn, vr = ry * g.cs;
+            const int j = jy0 + r;
+            const char *rowp = nullptr;
+            int exr = 0, eyr = 0;
+            if (IDENT) {
+                rowp = (const char *)kp.src + (int64_t)(j - kp.src_y0) * kp.src_pitch + (int64_t)ix0 * ESZ;
+            } else {
+                exr = kp.e_axj * j + kp.e_ax0 + kp.e_axi * ix0;
+                eyr = kp.e_ayj * j + kp.e_ay0 + kp.e_ayi * ix0;
+            }
+#pragma unroll
+            for (int k = 0; k < MAXN; ++k) {
+                const float rx = rx0 + (float)k;
+                const float ex = rx - 0.5f;
+                const float lenR = aai_overlap1_f32(yt[k + 1], yb[k + 1], ey);
+                const float lenT = aai_overlap1_f32(xlT, xrT, ex);
+                const float lenB = aai_overlap1_f32(xlB, xrB, ex);
+                const float u0 = fmaf(rx, g.cs, ur), v0 = fmaf(rx, g.sn, vr);
+                const float area = aai_cell_area_f32(g, u0, v0, lenT, lenB, lenL, lenR, worst);
+                lenL = lenR;
+                if (k < ncols) {
+                    const char *p;
+                    if (IDENT) {
+                        p = rowp + k * ESZ;
+                    } else {
+                        unsigned sx = (unsigned)(exr + k * kp.e_axi), sy = (unsigned)(eyr + k * kp.e_ayi);
+                        if (kp.scale != 1) {
+                            sx = __umulhi(sx, kp.div_magic);
+                            sy = __umulhi(sy, kp.div_magic);
+                        }
+                        p = (const char *)kp.src + (int64_t)((int)sy - kp.src_y0) * kp.src_pitch + (int64_t)sx * ESZ;
+                    }
+                    sumA += area;
+#pragma unroll
+                    for (int ch = 0; ch < NC; ++ch)
+                        acc[ch] = fmaf(LoadF<TI>::get(p + ch * (int)sizeof(TI)), area, acc[ch]);
+                }
+            }
+            xlT = xlB;
+            xrT = xrB;
+        }
+        // guard band of the quirk decision -> FP64
+        redo = worst < g.tau || sumA < 0.25f;
+    }
+    if (redo) {
+        double s64, a64[NC];
+        pixel_f64<TI, NC>(kp, cx, cy, ix0, ix1, jy0, jy1, s64, a64);
+        const bool ok = DBL_EPSILON < fabs(s64);
+#pragma unroll
+        for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, ok ? a64[ch] / s64 : 0.0);
+    } else {
+        const float inv = 1.0f / sumA;
+#pragma unroll
+        for (int ch = 0; ch < NC; ++ch) store_f<TO>(drow, x * NC + ch, acc[ch] * inv);
+    }
+}
+
+template <typename TI, typename TO, int NC>
+cudaError_t launch3(const AaiKernelParams &kp, cudaStream_t stream) {
+    const int rows = kp.row1 - kp.row0;
+    if (rows <= 0 || kp.dst_w <= 0) return cudaSuccess;
+    dim3 block(TILE_W, TILE_H);
+    dim3 grid((kp.dst_w + TILE_W - 1) / TILE_W, (rows + TILE_H - 1) / TILE_H);
+    if (kp.scale == 1 && kp.quadrant == 0)
+        overlap_kernel_f32<TI, TO, NC, true><<<grid, block, 0, stream>>>(kp);
+    else
+        overlap_kernel_f32<TI, TO, NC, false><<<grid, block, 0, stream>>>(kp);
+    return cudaGetLastError();
+}
+template <typename TI, typename TO>
+cudaError_t launch2(const AaiKernelParams &kp, cudaStream_t stream) {
+    return kp.channels == 1 ? launch3<TI, TO, 1>(kp, stream) : launch3<TI, TO, 3>(kp, stream);
+}
+template <typename TI>
+cudaError_t launch1(const AaiKernelParams &kp, int dst_dtype, cudaStream_t stream) {
+    switch (dst_dtype) {
+        case AAI_F64: return launch2<TI, double>(kp, stream);
+        case AAI_F32: return launch2<TI, float>(kp, stream);
+        case AAI_U8: return launch2<TI, uint8_t>(kp, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace
+
+#define AAI_CAT2(a, b) a##b
+#define AAI_CAT(a, b) AAI_CAT2(a, b)
+
+int AAI_CAT(aai_launch_overlap_f32_n, AAI_MAXN)(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (src_dtype) {
+        case AAI_F64: return (int)launch1<double>(kp, dst_dtype, st);
+        case AAI_F32: return (int)launch1<float>(kp, dst_dtype, st);
+        case AAI_U8: return (int)launch1<uint8_t>(kp, dst_dtype, st);
+        default: return (int)cudaErrorInvalidValue;
+    }
+}

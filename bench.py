@@ -225,7 +225,10 @@ def our_arm(args, cfg):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t.item()
 
-    arith = aai.ARITH_F32 if args.arith == "f32" else aai.ARITH_F64
+    if args.arith == "auto":
+        arith = aai.ARITH_F64 if cfg["dtype"] == "float64" else aai.ARITH_F32
+    else:
+        arith = aai.ARITH_F32 if args.arith == "f32" else aai.ARITH_F64
     np_dt = np.dtype(cfg["dtype"])
     t_dt = {"uint8": torch.uint8, "float32": torch.float32, "float64": torch.float64}[cfg["dtype"]]
     out_dt = torch.float64 if cfg["dtype"] == "float64" else torch.float32
@@ -423,7 +426,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", type=int, default=4, choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--arith", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--arith", default="auto", choices=["auto", "f64", "f32"],
+                    help="auto: FP32 kernel for float32/8-bit images, FP64 kernel for float64 images")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

@@ -61,8 +61,37 @@ extern "C" void aai_test_pair_areas_f32(double c, double s, double L, const doub
     const AaiShapeF g = make_shape_f(c, s, L);
     for (long long k = 0; k < n; ++k) {
         const double ix = std::nearbyint(cx[k]), iy = std::nearbyint(cy[k]);
-        bool unc = false;
-        out[k] = aai_pair_area_f32(g, (float)(cx[k] - ix), (float)(cy[k] - iy), i[k] - (int)ix, j[k] - (int)iy, unc);
-        flag[k] = unc ? 1 : 0;
+        float worst = 1.0f;
+        out[k] = aai_pair_area_f32(g, (float)(cx[k] - ix), (float)(cy[k] - iy), i[k] - (int)ix, j[k] - (int)iy, worst);
+        flag[k] = worst < g.tau ? 1 : 0;
     }
+}
+
+// Whole-image evaluation with the FP32 kernel's arithmetic (no FP64 fallback: flagged pixels are reported), TEST ONLY.
+extern "C" void aai_test_image_f32(double c, double s, double L, double offIx, double offIy, double isoX, double isoY,
+                                   double offX, double offY, int modW, int modH, int dstW, int dstH,
+                                   const double *mod /* modH x modW */, double *out, unsigned char *flag) {
+    const AaiShapeF g = make_shape_f(c, s, L);
+    const double reach = L * std::sqrt(2) / 2, hb = (L / 2) * (c + s), ext = hb + 0.5 + 1e-9;
+    for (int y = 0; y < dstH; ++y)
+        for (int x = 0; x < dstW; ++x) {
+            const double u = ((x + offIx) * L - isoX) + offX, v = ((y + offIy) * L - isoY) + offY;
+            const double cx = (u * c + v * s) + isoX, cy = (-u * s + v * c) + isoY;
+            int wx0 = std::max(0, (int)std::floor(cx - reach - 1)), wx1 = std::min((int)std::ceil(cx + reach + 1), modW - 1);
+            int wy0 = std::max(0, (int)std::floor(cy - reach - 1)), wy1 = std::min((int)std::ceil(cy + reach + 1), modH - 1);
+            int ix0 = std::max(wx0, (int)std::ceil(cx - ext)), ix1 = std::min(wx1, (int)std::floor(cx + ext));
+            int jy0 = std::max(wy0, (int)std::ceil(cy - ext)), jy1 = std::min(wy1, (int)std::floor(cy + ext));
+            const double rcx = std::nearbyint(cx), rcy = std::nearbyint(cy);
+            const float fx = (float)(cx - rcx), fy = (float)(cy - rcy);
+            float sumA = 0, acc = 0, worst = 1.0f;
+            for (int j = jy0; j <= jy1; ++j)
+                for (int i = ix0; i <= ix1; ++i) {
+                    const float a = aai_pair_area_f32(g, fx, fy, i - (int)rcx, j - (int)rcy, worst);
+                    sumA += a;
+                    acc = fmaf((float)mod[(size_t)j * modW + i], a, acc);
+                }
+            const size_t k = (size_t)y * dstW + x;
+            flag[k] = (worst < g.tau || sumA < 0.05f) ? 1 : 0;
+            out[k] = sumA > 0 ? (double)(acc * (1.0f / sumA)) : 0.0;
+        }
 }

@@ -19,6 +19,8 @@ def cellmath(built):
     subprocess.run([cxx, "-O2", "-fPIC", "-shared", "-o", so, os.path.join(HERE, "cell_math_host.cpp")], check=True)
     lib = C.CDLL(so)
     lib.aai_test_pair_areas.argtypes = [C.c_double] * 3 + [C.c_void_p] * 5 + [C.c_longlong]
+    lib.aai_test_pair_areas_f32.argtypes = [C.c_double] * 3 + [C.c_void_p] * 6 + [C.c_longlong]
+    lib.aai_test_image_f32.argtypes = [C.c_double] * 9 + [C.c_int] * 4 + [C.c_void_p] * 3
     return lib
 
 
@@ -85,3 +87,47 @@ def test_reference_quirk_is_reproduced(cellmath):
     assert 0.05 < differs.mean() < 0.5  # a sizeable share of touched pairs carries the quirk
     want = np.array([port.pair_area(_vertices(cx[k], cy[k], c, s, side / 2), int(i[k]), int(j[k])) for k in range(2000)])
     assert np.abs(got[:2000] - want).max() < 1e-11
+
+
+@pytest.mark.parametrize("theta,side", [(17.3, 2.7027027), (30.0, 2.7027027), (45.0, 1.7647059), (61.0, 1.7391304),
+                                        (5.0, 3.3), (85.0, 1.5), (73.0, 3.9)])
+def test_f32_cell_math_guard_band_catches_every_decision_flip(cellmath, theta, side):
+    """FP32 areas agree with the FP64 closed form to ~1e-6 on every pair the guard band does not flag; the pairs it
+    flags (redone in FP64 by the kernel) are rare."""
+    rng = np.random.default_rng(int(theta * 100))
+    c, s = np.cos(np.radians(theta)), np.sin(np.radians(theta))
+    n = 1_000_000
+    cx, cy = rng.uniform(100, 116, n), rng.uniform(100, 116, n)
+    i = np.floor(cx + rng.uniform(-side, side, n) + 0.5).astype(np.int32)
+    j = np.floor(cy + rng.uniform(-side, side, n) + 0.5).astype(np.int32)
+    a64, a32, flag = np.zeros(n), np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.uint8)
+    cellmath.aai_test_pair_areas(c, s, side, cx.ctypes.data, cy.ctypes.data, i.ctypes.data, j.ctypes.data,
+                                 a64.ctypes.data, n)
+    cellmath.aai_test_pair_areas_f32(c, s, side, cx.ctypes.data, cy.ctypes.data, i.ctypes.data, j.ctypes.data,
+                                     a32.ctypes.data, flag.ctypes.data, n)
+    keep = flag == 0
+    assert np.abs(a32 - a64)[keep].max() < 5e-6
+    assert flag.mean() < 2e-4
+
+
+def test_f32_image_with_exact_symmetry_ties(cellmath):
+    """45 degrees, scale 3, half-integer isocentre: the canvas centre pixel has cell centres exactly on the
+    footprint's centre lines (v0 == +-0).  Every pixel the guard band does not flag must be within 1e-5."""
+    import area_average_interpolation_b200 as aai
+    from oracle import port
+
+    w = h = 96
+    ratio, angle, iso = 1.7, 45.0, (47.5, 47.5)
+    rng = np.random.default_rng(7)
+    src = rng.uniform(0, 255, size=(h, w)).astype(np.float32).astype(np.float64)
+    p = aai.make_plan(w, h, 1.0, ratio, iso, angle)
+    mod = np.ascontiguousarray(np.repeat(np.repeat(src, p.scale, axis=0), p.scale, axis=1))
+    out = np.zeros((p.dst_h, p.dst_w))
+    flag = np.zeros((p.dst_h, p.dst_w), dtype=np.uint8)
+    cellmath.aai_test_image_f32(p.cos_t, p.sin_t, p.side, p.off_ix, p.off_iy, p.iso_x, p.iso_y, p.off_x, p.off_y,
+                                mod.shape[1], mod.shape[0], p.dst_w, p.dst_h, mod.ctypes.data, out.ctypes.data,
+                                flag.ctypes.data)
+    st, want, _ = port.run(src, 1.0, ratio, iso, angle)
+    err = np.abs(out - want) / np.maximum(np.abs(want), 1.0)
+    assert err[flag == 0].max() <= 1e-5
+    assert (flag[want > 0] == 1).mean() < 0.05

@@ -134,12 +134,73 @@ def test_f64_kernel_matches_oracle(aai, oracle, w, h, ratio, angle, iso):
 
 @pytest.mark.parametrize("w,h,ratio,angle,iso", SWEEP[:8])
 def test_fast_mode_matches_oracle(aai, oracle, w, h, ratio, angle, iso):
+    """Row f1 (fastAreaAverageInterpolation): a source pixel counts iff its CENTRE is in the footprint, so a centre
+    that lies exactly on a footprint edge is a tie the reference itself resolves by rounding noise (its 4-ray test has
+    a ~2e-14 px tolerance, below the 1e-13 rounding of its own vertices).  Pixels whose reference value changes under a
+    1e-11 isocentre shift are masked (T5); all others must match."""
     rng = np.random.default_rng(w * 31 + h)
     src = rng.uniform(0.0, 4096.0, size=(h, w))
     r = _run(aai, src, 1.0, ratio, iso, angle, mode=2)
     st, want, _ = oracle.run(src, 1.0, ratio, iso, angle, mode=2)
     assert st == 0 and want.shape == r.dst.shape
-    assert rel_err(r.dst, want).max() <= TOL_F64_REL
+    bad = rel_err(r.dst, want) > TOL_F64_REL
+    if bad.any():
+        case = dict(src_res=1.0, dst_res=ratio, iso=iso, angle=angle, mode=2)
+        mask = _conditioning_mask(oracle, src, case, want)
+        assert not (bad & ~mask).any(), int((bad & ~mask).sum())
+        assert bad.mean() < 0.02, float(bad.mean())
+
+
+# ---- FP32 kernel (north star: <= 1e-5 relative on float data, <= 0.5/255 absolute on 8-bit data) ----------------
+
+@pytest.mark.parametrize("w,h,ratio,angle,iso", SWEEP)
+def test_f32_kernel_matches_oracle_on_float_data(aai, oracle, w, h, ratio, angle, iso):
+    rng = np.random.default_rng(w * 104729 + h)
+    src = rng.uniform(0.0, 4096.0, size=(h, w)).astype(np.float32)
+    r = _run(aai, src, 1.0, ratio, iso, angle, arith=aai.ARITH_F32, out_dtype=np.float32)
+    st, want, wiso = oracle.run(src, 1.0, ratio, iso, angle)
+    assert st == 0 and want.shape == r.dst.shape and wiso == r.dst_isocenter
+    err = np.abs(r.dst.astype(np.float64) - want) / np.maximum(np.abs(want), 1e-30)
+    err[want == 0] = np.abs(r.dst[want == 0])
+    assert err.max() <= TOL_F32_REL, (float(err.max()), int((err > TOL_F32_REL).sum()))
+
+
+def test_f32_kernel_on_8bit_data_and_golden_vectors(aai, oracle):
+    z, meta = load_golden()
+    for case in meta["cases"]:
+        if case.get("degenerate") or case["mode"] != 1:
+            continue
+        src = golden_source(case)
+        if src.dtype == np.float64:
+            src = src.astype(np.float32)
+        r = _run(aai, src, case["src_res"], case["dst_res"], case["iso"], case["angle"], arith=aai.ARITH_F32,
+                 out_dtype=np.float32)
+        st, want, _ = oracle.run(src, case["src_res"], case["dst_res"], case["iso"], case["angle"])
+        tol = TOL_U8_ABS if src.dtype == np.uint8 else TOL_F32_REL * np.maximum(np.abs(want), 1e-30)
+        assert (np.abs(r.dst - want) <= tol).all(), case["name"]
+    rng = np.random.default_rng(12)
+    rgb = rng.integers(0, 256, size=(300, 260, 3), dtype=np.uint8)
+    for (ratio, angle, iso) in [(0.37, 30.0, (130.0, 150.0)), (1.7, 45.0, (129.5, 149.5)), (0.9, 200.0, (10.0, 10.0))]:
+        r = _run(aai, rgb, 1.0, ratio, iso, angle, arith=aai.ARITH_F32, out_dtype=np.float32)
+        for c in range(3):
+            st, want, _ = oracle.run(rgb, 1.0, ratio, iso, angle, channel=c)
+            assert np.abs(r.dst[..., c] - want).max() <= TOL_U8_ABS, (ratio, angle, c)
+        r8 = _run(aai, rgb, 1.0, ratio, iso, angle, arith=aai.ARITH_F32, out_dtype=np.uint8)
+        assert np.abs(r8.dst.astype(np.float64) - r.dst).max() <= 0.5 + 1e-3  # round half up of the real value
+
+
+def test_f32_kernel_symmetric_ties_and_near_axis_angles(aai, oracle):
+    """Exactly symmetric geometry (cell centres on the footprint's centre lines: sign ties) and angles where the
+    FP32 kernel must hand over to FP64 (1/sin or 1/cos > 20)."""
+    rng = np.random.default_rng(77)
+    src = rng.uniform(0.0, 255.0, size=(256, 256)).astype(np.float32)
+    for (ratio, angle, iso) in [(1.7, 45.0, (127.5, 127.5)), (0.5, 45.0, (127.5, 127.5)), (0.6, 1.0, (128.0, 128.0)),
+                                (0.6, 88.5, (128.0, 128.0)), (0.6, 5.0, (128.0, 128.0))]:
+        r = _run(aai, src, 1.0, ratio, iso, angle, arith=aai.ARITH_F32, out_dtype=np.float32)
+        st, want, _ = oracle.run(src, 1.0, ratio, iso, angle)
+        err = np.abs(r.dst - want) / np.maximum(np.abs(want), 1e-30)
+        err[want == 0] = np.abs(r.dst[want == 0])
+        assert err.max() <= TOL_F32_REL, (ratio, angle, float(err.max()))
 
 
 def test_u8_rgb_and_f32_sources(aai, oracle):
@@ -260,10 +321,18 @@ def test_full_size_cfg4_sample_rows_and_properties(aai, oracle):
     src = synthetic_image(W, W, np.float32, 20201 + 4)
     src_t = torch.from_numpy(src).cuda()
     out = _device_run(aai, plan, src_t, torch.float64).cpu().numpy()
+    out32 = _device_run(aai, plan, src_t, torch.float32, arith=aai.ARITH_F32).cpu().numpy()
     for row in (0, 1, 1700, 3795, 3796, 6000, 7589, 7590):
         st, want, _ = oracle.run(src, 1.0, 0.37, (8192.0, 8192.0), 17.3, rows=(row, row + 1))
         err = rel_err(out[row:row + 1], want)
         assert err.max() <= TOL_F64_REL, (row, float(err.max()))
+        e32 = np.abs(out32[row:row + 1] - want) / np.maximum(np.abs(want), 1e-30)
+        e32[want == 0] = np.abs(out32[row:row + 1][want == 0])
+        assert e32.max() <= TOL_F32_REL, (row, float(e32.max()))
+    # FP32 and FP64 kernels agree over the WHOLE canvas (the FP64 one is oracle-checked on the sample rows above)
+    whole = np.abs(out32 - out) / np.maximum(np.abs(out), 1e-30)
+    whole[out == 0] = np.abs(out32[out == 0])
+    assert whole.max() <= TOL_F32_REL, float(whole.max())
     frac = (out != 0).mean()
     assert 0.62 < frac < 0.65  # covered fraction 0.638
     ones = _device_run(aai, plan, torch.ones(W, W, dtype=torch.float32, device="cuda"), torch.float64)
