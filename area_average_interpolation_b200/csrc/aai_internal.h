@@ -41,6 +41,8 @@ AaiKernelParams aai_make_kernel_params(const aai_plan &plan, const aai_image &sr
 int aai_launch_overlap(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_separable(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_fast(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
+// aai_kernels_sep.cu: TMA-staged separable kernel; returns cudaErrorNotSupported when its fast path does not apply
+int aai_launch_separable_tma(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);
 // aai_kernels_f32.cu, one translation unit per maximum cell count per axis
 int aai_launch_overlap_f32_n4(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_overlap_f32_n5(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);

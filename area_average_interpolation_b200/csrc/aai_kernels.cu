@@ -188,7 +188,9 @@ int aai_launch_overlap(const AaiKernelParams &kp, int arith, int src_dtype, int 
     return (int)launch_any(K_OVERLAP, kp, src_dtype, dst_dtype, (cudaStream_t)stream);
 }
 int aai_launch_separable(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream) {
-    (void)arith;
+    // TMA-staged two-pass kernel when its preconditions hold, else direct taps
+    const int e = aai_launch_separable_tma(kp, arith, src_dtype, dst_dtype, stream);
+    if (e != (int)cudaErrorNotSupported) return e;
     return (int)launch_any(K_SEPARABLE, kp, src_dtype, dst_dtype, (cudaStream_t)stream);
 }
 int aai_launch_fast(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream) {
