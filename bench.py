@@ -365,7 +365,7 @@ def our_arm(args, cfg):
     alg_bytes = (W * H * CH * np_dt.itemsize + plan.dst_w * plan.dst_h * CH * host_dst.element_size()) * cfg["batch"]
     kernel_ms = ms_step / launches_per_step if cfg["batch"] > 1 else ms_step
     if plan.axis_aligned:
-        per_launch = alg_bytes / cfg["batch"] / world
+        per_launch = alg_bytes / cfg["batch"] if cfg["batch"] > 1 else alg_bytes / world
         achieved = per_launch / (kernel_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "traffic": None, "peak_source": hbm_src,

@@ -164,8 +164,9 @@ int aai_run_host_band(const aai_plan *plan, int mode, int arith, const aai_image
 int64_t aai_launch_count(void);
 
 /* Device-side breakdown [ms] of the last aai_run_host() on this thread, from CUDA events on the per-device
- * streams (max over devices): host->device copies, kernels, device->host copies.  Returns AAI_OK or
- * AAI_ERR_ARGUMENT if no run has completed. */
+ * streams (max over devices): host->device copies, kernels, device->host copies.  Large bands are pipelined
+ * (chunked upload / kernel / download on three streams): the phases overlap, so the whole call is reported in
+ * *h2d_ms and the other two are 0.  Returns AAI_OK or AAI_ERR_ARGUMENT if no run has completed. */
 int aai_last_host_timing(float *h2d_ms, float *kernel_ms, float *d2h_ms);
 
 #ifdef __cplusplus
