@@ -99,6 +99,9 @@ def lib() -> C.CDLL:
         L.aai_run_device.restype = C.c_int
         L.aai_run_device.argtypes = [C.POINTER(Plan), C.c_int, C.c_int, C.POINTER(Image), C.POINTER(Image),
                                      C.c_int64, C.c_int64, C.c_int, C.c_void_p]
+        L.aai_run_device_batch.restype = C.c_int
+        L.aai_run_device_batch.argtypes = [C.POINTER(Plan), C.c_int, C.c_int, C.POINTER(Image), C.POINTER(Image),
+                                           C.c_int, C.c_int, C.c_void_p]
         L.aai_run_host.restype = C.c_int
         L.aai_run_host.argtypes = [C.POINTER(Plan), C.c_int, C.c_int, C.POINTER(Image), C.POINTER(Image),
                                    C.POINTER(C.c_int), C.c_int]
@@ -216,6 +219,14 @@ def run_device(plan: Plan, src_img: Image, dst_img: Image, row0: int = 0, row1: 
                                 C.c_void_p(stream)))
 
 
+def run_device_batch(plan: Plan, src_imgs: Sequence[Image], dst_imgs: Sequence[Image], mode: int = MODE_AREA_AVERAGE,
+                     arith: int = ARITH_F64, device: int = 0, stream: int = 0) -> None:
+    """``aai_run_device_batch``: a batch of images sharing one plan (one launch when equally strided + axis-aligned)."""
+    n = len(src_imgs)
+    sa, da = (Image * n)(*src_imgs), (Image * n)(*dst_imgs)
+    _check(lib().aai_run_device_batch(C.byref(plan), int(mode), int(arith), sa, da, n, int(device), C.c_void_p(stream)))
+
+
 def run_host(plan: Plan, src: np.ndarray, dst: np.ndarray, mode: int = MODE_AREA_AVERAGE, arith: int = ARITH_F64,
              devices: Optional[Sequence[int]] = None) -> None:
     """``aai_run_host``: the reference call with host buffers (H2D, kernels on per-device streams, D2H)."""
@@ -293,6 +304,6 @@ class AreaAverageInterpolation:
 
 __all__ = [
     "AreaAverageInterpolation", "Result", "Plan", "Image", "AaiError", "make_plan", "partition_rows",
-    "band_source_window", "covered_pixels", "device_count", "launch_count", "last_host_timing", "run_device",
+    "band_source_window", "covered_pixels", "device_count", "launch_count", "last_host_timing", "run_device", "run_device_batch",
     "run_host", "run_host_band", "tensor_image", "status_string", "last_error", "lib", "LIB_PATH",
 ]

@@ -323,6 +323,49 @@ static int check_host_images(const char *who, const aai_plan *plan, const aai_im
     return AAI_OK;
 }
 
+int aai_run_device_batch(const aai_plan *plan, int mode, int arith, const aai_image *srcs, const aai_image *dsts,
+                         int n_images, int device, void *stream) {
+    if (!plan || !srcs || !dsts || n_images <= 0) {
+        aai_set_error("aai_run_device_batch: bad argument");
+        return AAI_ERR_ARGUMENT;
+    }
+    if (plan->status != AAI_OK) return plan->status;
+    // one launch when the images form an equally strided stack of whole images and the separable TMA path applies
+    bool uniform = n_images > 1 && plan->axis_aligned && mode == AAI_MODE_AREA_AVERAGE && image_ok(&srcs[0]) &&
+                   image_ok(&dsts[0]) && srcs[0].y0 == 0 && srcs[0].rows == srcs[0].height && dsts[0].y0 == 0 &&
+                   dsts[0].rows == dsts[0].height && srcs[0].width == plan->src_w && srcs[0].height == plan->src_h &&
+                   dsts[0].width == plan->dst_w && dsts[0].height == plan->dst_h && srcs[0].channels == 1 &&
+                   dsts[0].channels == 1;
+    const int64_t sstride = uniform ? (const char *)srcs[1].data - (const char *)srcs[0].data : 0;
+    const int64_t dstride = uniform ? (const char *)dsts[1].data - (const char *)dsts[0].data : 0;
+    for (int k = 1; uniform && k < n_images; ++k) {
+        const aai_image &a = srcs[k], &b = dsts[k];
+        uniform = a.data == (const char *)srcs[0].data + k * sstride && b.data == (char *)dsts[0].data + k * dstride &&
+                  a.pitch_bytes == srcs[0].pitch_bytes && b.pitch_bytes == dsts[0].pitch_bytes &&
+                  a.dtype == srcs[0].dtype && b.dtype == dsts[0].dtype && a.width == srcs[0].width &&
+                  a.height == srcs[0].height && a.y0 == 0 && a.rows == a.height && b.width == dsts[0].width &&
+                  b.height == dsts[0].height && b.y0 == 0 && b.rows == b.height && a.channels == 1 && b.channels == 1;
+    }
+    if (uniform && sstride > 0 && dstride > 0) {
+        AAI_CUDA(cudaSetDevice(device));
+        AaiKernelParams kp = aai_make_kernel_params(*plan, srcs[0], dsts[0], 0, plan->dst_h);
+        kp.batch = n_images;
+        kp.src_batch_stride = sstride;
+        kp.dst_batch_stride = dstride;
+        const int e = aai_launch_separable_tma(kp, arith, srcs[0].dtype, dsts[0].dtype, stream);
+        if (e == (int)cudaSuccess) {
+            g_launches.fetch_add(1);
+            return AAI_OK;
+        }
+        if (e != (int)cudaErrorNotSupported) return cuda_fail((cudaError_t)e, "batched separable kernel launch");
+    }
+    for (int k = 0; k < n_images; ++k) {
+        const int r = aai_run_device(plan, mode, arith, &srcs[k], &dsts[k], 0, plan->dst_h, device, stream);
+        if (r != AAI_OK) return r;
+    }
+    return AAI_OK;
+}
+
 int aai_run_host_band(const aai_plan *plan, int mode, int arith, const aai_image *src, const aai_image *dst,
                       int64_t row0, int64_t row1, int device, void *stream, int synchronize) {
     int r = check_host_images("aai_run_host_band", plan, src, dst, false);

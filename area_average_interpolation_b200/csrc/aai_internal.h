@@ -32,6 +32,9 @@ struct AaiKernelParams {
     void *dst;
     int64_t dst_pitch;
     int32_t dst_y0, row0, row1;
+    // batch of equally strided images sharing one plan (separable TMA path only; 0/1 = single image)
+    int32_t batch;
+    int64_t src_batch_stride, dst_batch_stride;
 };
 
 AaiKernelParams aai_make_kernel_params(const aai_plan &plan, const aai_image &src, const aai_image &dst,

@@ -10,6 +10,8 @@
 // intermediate tile, then columns (vertical taps, weights broadcast from shared memory) to the coalesced store.
 // Several CTAs are resident per SM, so one CTA's TMA load overlaps the other CTAs' passes.
 //
+// A batch of equally strided images is ONE launch: the tensor map is rank 3 (x, y, image), blockIdx.y = image.
+//
 // Fast path preconditions (checked by the host launcher, otherwise the direct-tap kernel in aai_kernels.cu runs):
 // scale 1, quadrant 0, one channel, 16-byte aligned rows, footprint side small enough for a <=256-wide TMA box.
 // TMA tile coordinates must be 16-byte aligned in the innermost dimension: the window origin is rounded down.
@@ -53,11 +55,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+// (x, y, image) box of a rank-3 tensor map: a batch of equally strided images is one tensor
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+            "r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(SEP_THREADS)
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(bar, (uint32_t)(sp.bw * sp.bh * sizeof(TI)));
-        tma_load_2d(tile, &tmap, bar, ox, oy - kp.src_y0);
+        tma_load_3d(tile, &tmap, bar, ox, oy - kp.src_y0, (int)blockIdx.y);
     }
 
     // while the TMA load is in flight: per-column weights (registers) and per-row weights (shared memory)
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(SEP_THREADS)
             for (int t = 0; t < MAXT; ++t) acc += wyw[yo * MAXT + t] * hbuf[(size_t)(rf + t) * TW + xo];
             const TA total = sumx * wys[yo];
             const double out = ((double)total > DBL_EPSILON) ? (double)(acc / total) : 0.0;  // Source.cpp:577
-            char *drow = (char *)kp.dst + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
+            char *drow = (char *)kp.dst + (int64_t)blockIdx.y * kp.dst_batch_stride + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
             store_dst<TO>(drow, x, out);
         }
     }
@@ -242,11 +245,14 @@ cudaError_t launch_sep(const AaiKernelParams &kp, cudaStream_t stream) {
     if (smem > 200 * 1024) return cudaErrorNotSupported;
 
     CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {(cuuint64_t)kp.src_w, (cuuint64_t)kp.src_rows};
-    const cuuint64_t gstride[1] = {(cuuint64_t)kp.src_pitch};
-    const cuuint32_t box[2] = {(cuuint32_t)sp.bw, (cuuint32_t)sp.bh};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(&tmap, tmap_dtype<TI>(), 2, const_cast<void *>(kp.src), gdim, gstride, box, estr,
+    const int batch = kp.batch > 0 ? kp.batch : 1;
+    const cuuint64_t gdim[3] = {(cuuint64_t)kp.src_w, (cuuint64_t)kp.src_rows, (cuuint64_t)batch};
+    const cuuint64_t gstride[2] = {(cuuint64_t)kp.src_pitch,
+                                   (cuuint64_t)(batch > 1 ? kp.src_batch_stride : kp.src_pitch * (int64_t)kp.src_rows)};
+    const cuuint32_t box[3] = {(cuuint32_t)sp.bw, (cuuint32_t)sp.bh, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (gstride[1] % 16 != 0) return cudaErrorNotSupported;
+    const CUresult r = enc(&tmap, tmap_dtype<TI>(), 3, const_cast<void *>(kp.src), gdim, gstride, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorNotSupported;
@@ -257,16 +263,18 @@ cudaError_t launch_sep(const AaiKernelParams &kp, cudaStream_t stream) {
     auto kernel = separable_tma_kernel<TI, TO, TA, TW, MAXT>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kernel<<<sp.tiles_x * tiles_y, SEP_THREADS, smem, stream>>>(tmap, kp, sp);
+    kernel<<<dim3(sp.tiles_x * tiles_y, batch), SEP_THREADS, smem, stream>>>(tmap, kp, sp);
     return cudaGetLastError();
 }
 
 template <typename TI, typename TO, typename TA>
 cudaError_t launch_sep_shape(const AaiKernelParams &kp, cudaStream_t stream) {
     const double L = 2.0 * kp.shape.half;
-    const int taps = (int)floor(L) + 2;
+    // an interval of length L meets at most ceil(L)+1 unit cells with positive length
+    const int taps = (int)ceil(L - 1e-12) + 1;
     cudaError_t e = cudaErrorNotSupported;
-    if (taps <= 4) e = launch_sep<TI, TO, TA, 64, 4>(kp, stream);
+    if (taps <= 3) e = launch_sep<TI, TO, TA, 64, 3>(kp, stream);
+    if (e == cudaErrorNotSupported && taps <= 4) e = launch_sep<TI, TO, TA, 64, 4>(kp, stream);
     if (e == cudaErrorNotSupported && taps <= 6) e = launch_sep<TI, TO, TA, 64, 6>(kp, stream);
     if (e == cudaErrorNotSupported && taps <= 10) e = launch_sep<TI, TO, TA, 32, 10>(kp, stream);
     return e;

@@ -146,6 +146,13 @@ int aai_image_download(const aai_image *host_img, const aai_image *device_img, i
 int aai_run_device(const aai_plan *plan, int mode, int arith, const aai_image *src, const aai_image *dst,
                    int64_t row0, int64_t row1, int device, void *stream);
 
+/* A batch of images that share one plan (BASELINE config 5: 256 slices).  When the images are whole, single-channel,
+ * equally strided in memory (srcs[k].data = srcs[0].data + k*stride, same for dsts) and the plan is axis-aligned,
+ * the whole batch is ONE kernel launch (rank-3 TMA tensor map, one grid row per image); otherwise the images are
+ * enqueued one after the other.  Device images, asynchronous on `stream`. */
+int aai_run_device_batch(const aai_plan *plan, int mode, int arith, const aai_image *srcs, const aai_image *dsts,
+                         int n_images, int device, void *stream);
+
 /* The reference call end to end with HOST buffers: upload (each device gets its band's halo), kernels on
  * per-device streams, download.  `devices` = NULL / n_devices = 0 means device 0.  No NCCL: bands are
  * independent.  Blocks until dst is complete. */

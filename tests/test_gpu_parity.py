@@ -262,6 +262,35 @@ def test_multi_device_host_path_if_available(aai, oracle):
     assert np.array_equal(one.dst, many.dst)
 
 
+def test_batch_of_slices_is_one_launch_and_matches_per_image_runs(aai, oracle):
+    """BASELINE config 5 in small: a stack of equally strided slices, 0.5x axis-aligned -> one kernel launch."""
+    import torch
+
+    n, w, h = 5, 200, 168
+    plan = aai.make_plan(w, h, 1.0, 0.5, (100.0, 84.0), 0.0)
+    src = torch.rand(n, h, w, dtype=torch.float32, device="cuda") * 4096
+    dst = torch.empty(n, plan.dst_h, plan.dst_w, dtype=torch.float32, device="cuda")
+    ref = torch.empty_like(dst)
+    stream = torch.cuda.current_stream().cuda_stream
+    before = aai.launch_count()
+    aai.run_device_batch(plan, [aai.tensor_image(src[k]) for k in range(n)], [aai.tensor_image(dst[k]) for k in range(n)],
+                         arith=aai.ARITH_F32, stream=stream)
+    assert aai.launch_count() == before + 1
+    for k in range(n):
+        aai.run_device(plan, aai.tensor_image(src[k]), aai.tensor_image(ref[k]), arith=aai.ARITH_F32, stream=stream)
+    torch.cuda.synchronize()
+    assert torch.equal(dst, ref)
+    st, want, _ = oracle.run(src[3].cpu().numpy(), 1.0, 0.5, (100.0, 84.0), 0.0)
+    assert (np.abs(dst[3].cpu().numpy() - want) <= TOL_F32_REL * np.maximum(np.abs(want), 1e-30)).all()
+    # not equally strided (reversed order) or rotated: falls back to one launch per image, same results
+    order = [4, 2, 0]
+    out2 = torch.empty(3, plan.dst_h, plan.dst_w, dtype=torch.float32, device="cuda")
+    aai.run_device_batch(plan, [aai.tensor_image(src[k]) for k in order], [aai.tensor_image(out2[i]) for i in range(3)],
+                         arith=aai.ARITH_F32, stream=stream)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, ref[order])
+
+
 def test_argument_errors_are_reported_not_crashed(aai):
     import torch
 
