@@ -177,6 +177,89 @@ AAI_HD float aai_cell_area_f32(const AaiShapeF &g, float u0, float v0, float len
     return need > 0.0f ? quirk : area;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Packed variant: two horizontally adjacent cells per call on Blackwell's packed FP32 pipe (FFMA2 / FMUL2 / FADD2,
+// `fma.rn.f32x2` -- sm_100a).  The kernel is instruction-issue bound, and every multiply/add of the cell math is
+// independent between cells, so two cells share one instruction.  Same arithmetic, operation by operation, as
+// aai_cell_area_f32 (the host build of this header evaluates the two lanes with scalar fmaf).
+// ------------------------------------------------------------------------------------------------------------
+struct AaiF2 {
+    float x, y;
+};
+AAI_HD AaiF2 aai_f2(float x, float y) {
+    AaiF2 r;
+    r.x = x;
+    r.y = y;
+    return r;
+}
+AAI_HD AaiF2 aai_f2(float v) { return aai_f2(v, v); }
+#if defined(__CUDA_ARCH__)
+AAI_HD AaiF2 aai_fma2(AaiF2 a, AaiF2 b, AaiF2 c) {
+    const float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+    return aai_f2(r.x, r.y);
+}
+AAI_HD AaiF2 aai_mul2(AaiF2 a, AaiF2 b) {
+    const float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    return aai_f2(r.x, r.y);
+}
+AAI_HD AaiF2 aai_add2(AaiF2 a, AaiF2 b) {
+    const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    return aai_f2(r.x, r.y);
+}
+#else
+AAI_HD AaiF2 aai_fma2(AaiF2 a, AaiF2 b, AaiF2 c) { return aai_f2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+AAI_HD AaiF2 aai_mul2(AaiF2 a, AaiF2 b) { return aai_f2(a.x * b.x, a.y * b.y); }
+AAI_HD AaiF2 aai_add2(AaiF2 a, AaiF2 b) { return aai_f2(a.x + b.x, a.y + b.y); }
+#endif
+AAI_HD AaiF2 aai_sub2(AaiF2 a, AaiF2 b) { return aai_fma2(b, aai_f2(-1.0f), a); }  // a - b as one FFMA2
+AAI_HD float aai_flip(float v, float sign_of) {  // v with its sign flipped when sign_of is negative (one LOP3)
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(__float_as_int(v) ^ (__float_as_int(sign_of) & 0x80000000));
+#else
+    return signbit(sign_of) ? -v : v;
+#endif
+}
+
+// cells k (lane .x) and k+1 (lane .y) of one row; arguments as in aai_cell_area_f32
+AAI_HD AaiF2 aai_cell_area_f32x2(const AaiShapeF &g, AaiF2 u0, AaiF2 v0, AaiF2 lenT, AaiF2 lenB, AaiF2 lenL,
+                                 AaiF2 lenR, float &worst) {
+    const AaiF2 ca = aai_sub2(aai_f2(copysignf(g.half, u0.x), copysignf(g.half, u0.y)), u0);  // su * a
+    const AaiF2 cb = aai_sub2(aai_f2(copysignf(g.half, v0.x), copysignf(g.half, v0.y)), v0);
+    const AaiF2 cs2 = aai_f2(g.cs), sn2 = aai_f2(g.sn);
+    const AaiF2 vx = aai_fma2(ca, cs2, aai_mul2(cb, sn2));
+    const AaiF2 vy = aai_fma2(cb, cs2, aai_mul2(ca, aai_f2(-g.sn)));
+    const AaiF2 sum4 = aai_add2(aai_add2(lenT, lenB), aai_add2(lenL, lenR));
+    const AaiF2 cross = aai_fma2(vy, aai_sub2(lenT, lenB), aai_mul2(vx, aai_sub2(lenL, lenR)));
+    const AaiF2 area = aai_fma2(aai_f2(0.25f), sum4, aai_mul2(aai_f2(0.5f), cross));
+    // a = su * ca: |a| = |ca|, sign(a) = sign(ca) ^ sign(u0)
+    const AaiF2 aa = aai_f2(fabsf(ca.x), fabsf(ca.y));
+    const bool neg_x = aai_sign_product_positive(ca.x, u0.x, -1.0f);  // a < 0 (sign bits)
+    const bool neg_y = aai_sign_product_positive(ca.y, u0.y, -1.0f);
+    const AaiF2 wx = aai_f2(aai_flip(vx.x, v0.x), aai_flip(vx.y, v0.y));
+    const AaiF2 wy = aai_f2(aai_flip(vy.x, v0.x), aai_flip(vy.y, v0.y));
+    // lambda = su*sv*sign(a) = sign(ca)*sign(v0) > 0: the isolated corner is the top-right one (W frame)
+    const bool tr_x = aai_sign_product_positive(ca.x, v0.x, 1.0f), tr_y = aai_sign_product_positive(ca.y, v0.y, 1.0f);
+    const AaiF2 p = aai_f2(tr_x ? wx.x : wy.x, tr_y ? wx.y : wy.y);
+    const AaiF2 q = aai_f2(tr_x ? wy.x : wx.x, tr_y ? wy.y : wx.y);
+    const AaiF2 kk = aai_f2(tr_x ? g.k_sc : g.k_cs, tr_y ? g.k_sc : g.k_cs);
+    const AaiF2 m1 = aai_add2(aa, aai_f2(-g.thr));
+    const AaiF2 m2 = aai_sub2(aai_f2(g.m), aa);
+    const AaiF2 m3 = aai_add2(p, aai_f2(-0.5f));
+    const AaiF2 m4 = aai_add2(q, aai_f2(0.5f));
+    const AaiF2 m5v = aai_fma2(kk, m3, aai_add2(q, aai_f2(-0.5f)));
+    const float m5x = neg_x ? 1.0f : m5v.x, m5y = neg_y ? 1.0f : m5v.y;
+    const float need_x = fminf(fminf(fminf(m1.x, m2.x), fminf(m3.x, m4.x)), m5x);
+    const float need_y = fminf(fminf(fminf(m1.y, m2.y), fminf(m3.y, m4.y)), m5y);
+    worst = fminf(worst, fminf(fabsf(need_x), fabsf(need_y)));
+    const AaiF2 one = aai_f2(1.0f);
+    const AaiF2 tri = aai_mul2(aai_mul2(aai_f2(0.5f), aai_fma2(m2, aai_f2(-g.inv_c), one)), aai_fma2(m2, aai_f2(-g.inv_s), one));
+    const AaiF2 pent = aai_sub2(one, tri);
+    AaiF2 out;
+    out.x = need_x > 0.0f ? (neg_x ? tri.x : pent.x) : area.x;
+    out.y = need_y > 0.0f ? (neg_y ? tri.y : pent.y) : area.y;
+    return out;
+}
+
 // Stand-alone FP32 form for one pair (tests): (fx, fy) = footprint centre minus the nearest integer lattice point,
 // (di, dj) = cell index relative to that lattice point.
 AAI_HD float aai_pair_area_f32(const AaiShapeF &g, float fx, float fy, int di, int dj, float &worst) {

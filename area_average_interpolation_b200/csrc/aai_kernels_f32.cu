@@ -9,6 +9,8 @@
 //   * the footprint centre is computed in FP64 exactly like the reference (212-219) and split into the nearest
 //     lattice point + an FP32 fraction, so every FP32 quantity is O(L) with ~1e-7 absolute error;
 //   * side lengths |side ∩ footprint| are differences of FADD.SAT (no min/max on the half-rate ALU pipe);
+//   * the kernel is instruction-issue bound, so horizontally adjacent cells are evaluated two at a time on
+//     Blackwell's packed FP32 instructions (FFMA2 / FMUL2 / FADD2 = fma.rn.f32x2, sm_100a);
 //   * the reference's shape-2/4 quirk is decided branch-free (aai_cell.cuh); the smallest decision margin of the
 //     pixel is tracked and, when it falls inside the FP32 guard band, or when the pixel's total overlap is tiny
 //     (border slivers need relative accuracy), the pixel is redone in FP64 (pixel_f64) -- FP32 rounding can never
@@ -110,16 +112,8 @@ __global__ void __launch_bounds__(TILE_W *TILE_H)
                 exr = kp.e_axj * j + kp.e_ax0 + kp.e_axi * ix0;
                 eyr = kp.e_ayj * j + kp.e_ay0 + kp.e_ayi * ix0;
             }
-#pragma unroll
-            for (int k = 0; k < MAXN; ++k) {
-                const float rx = rx0 + (float)k;
-                const float ex = rx - 0.5f;
-                const float lenR = aai_overlap1_f32(yt[k + 1], yb[k + 1], ey);
-                const float lenT = aai_overlap1_f32(xlT, xrT, ex);
-                const float lenB = aai_overlap1_f32(xlB, xrB, ex);
-                const float u0 = fmaf(rx, g.cs, ur), v0 = fmaf(rx, g.sn, vr);
-                const float area = aai_cell_area_f32(g, u0, v0, lenT, lenB, lenL, lenR, worst);
-                lenL = lenR;
+            // load + accumulate one cell (predicated: columns beyond the footprint box are never read)
+            auto take = [&](int k, float area) {
                 if (k < ncols) {
                     const char *p;
                     if (IDENT) {
@@ -137,6 +131,33 @@ __global__ void __launch_bounds__(TILE_W *TILE_H)
                     for (int ch = 0; ch < NC; ++ch)
                         acc[ch] = fmaf(LoadF<TI>::get(p + ch * (int)sizeof(TI)), area, acc[ch]);
                 }
+            };
+            // cells two at a time on the packed FP32 pipe (FFMA2/FMUL2/FADD2), a last odd cell on the scalar one
+#pragma unroll
+            for (int k = 0; k + 1 < MAXN; k += 2) {
+                const float rxa = rx0 + (float)k, rxb = rx0 + (float)(k + 1);
+                const float exa = rxa - 0.5f, exb = rxb - 0.5f;
+                const float lenM = aai_overlap1_f32(yt[k + 1], yb[k + 1], ey);
+                const float lenR = aai_overlap1_f32(yt[k + 2], yb[k + 2], ey);
+                const AaiF2 lT = aai_f2(aai_overlap1_f32(xlT, xrT, exa), aai_overlap1_f32(xlT, xrT, exb));
+                const AaiF2 lB = aai_f2(aai_overlap1_f32(xlB, xrB, exa), aai_overlap1_f32(xlB, xrB, exb));
+                const AaiF2 rx2 = aai_f2(rxa, rxb);
+                const AaiF2 u0 = aai_fma2(rx2, aai_f2(g.cs), aai_f2(ur)), v0 = aai_fma2(rx2, aai_f2(g.sn), aai_f2(vr));
+                const AaiF2 area = aai_cell_area_f32x2(g, u0, v0, lT, lB, aai_f2(lenL, lenM), aai_f2(lenM, lenR), worst);
+                lenL = lenR;
+                take(k, area.x);
+                take(k + 1, area.y);
+            }
+            if (MAXN & 1) {
+                constexpr int k = MAXN - 1;
+                const float rx = rx0 + (float)k;
+                const float ex = rx - 0.5f;
+                const float lenR = aai_overlap1_f32(yt[k + 1], yb[k + 1], ey);
+                const float lenT = aai_overlap1_f32(xlT, xrT, ex);
+                const float lenB = aai_overlap1_f32(xlB, xrB, ex);
+                const float u0 = fmaf(rx, g.cs, ur), v0 = fmaf(rx, g.sn, vr);
+                const float area = aai_cell_area_f32(g, u0, v0, lenT, lenB, lenL, lenR, worst);
+                take(k, area);
             }
             xlT = xlB;
             xrT = xrB;

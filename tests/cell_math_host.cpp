@@ -95,3 +95,33 @@ extern "C" void aai_test_image_f32(double c, double s, double L, double offIx, d
             out[k] = sumA > 0 ? (double)(acc * (1.0f / sumA)) : 0.0;
         }
 }
+
+
+// Packed (two cells per call) variant: evaluates cells (i, j) and (i+1, j); returns lane .x in out0, lane .y in out1.
+extern "C" void aai_test_pair_areas_f32x2(double c, double s, double L, const double *cx, const double *cy, const int *i,
+                                          const int *j, float *out0, float *out1, unsigned char *flag, long long n) {
+    const AaiShapeF g = make_shape_f(c, s, L);
+    for (long long k = 0; k < n; ++k) {
+        const double ix = std::nearbyint(cx[k]), iy = std::nearbyint(cy[k]);
+        const float fx = (float)(cx[k] - ix), fy = (float)(cy[k] - iy);
+        const int di = i[k] - (int)ix, dj = j[k] - (int)iy;
+        const float rx = (float)di - fx, ry = (float)dj - fy;
+        float xlT, xrT, xlB, xrB, y0t, y0b, y1t, y1b, y2t, y2b;
+        aai_chord_h_f32(g, ry - 0.5f, xlT, xrT);
+        aai_chord_h_f32(g, ry + 0.5f, xlB, xrB);
+        aai_chord_v_f32(g, rx - 0.5f, y0t, y0b);
+        aai_chord_v_f32(g, rx + 0.5f, y1t, y1b);
+        aai_chord_v_f32(g, rx + 1.5f, y2t, y2b);
+        const float ey = ry - 0.5f;
+        const float l0 = aai_overlap1_f32(y0t, y0b, ey), l1 = aai_overlap1_f32(y1t, y1b, ey), l2 = aai_overlap1_f32(y2t, y2b, ey);
+        const AaiF2 lenT = aai_f2(aai_overlap1_f32(xlT, xrT, rx - 0.5f), aai_overlap1_f32(xlT, xrT, rx + 0.5f));
+        const AaiF2 lenB = aai_f2(aai_overlap1_f32(xlB, xrB, rx - 0.5f), aai_overlap1_f32(xlB, xrB, rx + 0.5f));
+        const AaiF2 u0 = aai_f2(fmaf(rx, g.cs, -ry * g.sn), fmaf(rx + 1.0f, g.cs, -ry * g.sn));
+        const AaiF2 v0 = aai_f2(fmaf(rx, g.sn, ry * g.cs), fmaf(rx + 1.0f, g.sn, ry * g.cs));
+        float worst = 1.0f;
+        const AaiF2 a = aai_cell_area_f32x2(g, u0, v0, lenT, lenB, aai_f2(l0, l1), aai_f2(l1, l2), worst);
+        out0[k] = a.x;
+        out1[k] = a.y;
+        flag[k] = worst < g.tau ? 1 : 0;
+    }
+}
