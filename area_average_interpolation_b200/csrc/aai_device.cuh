@@ -132,19 +132,20 @@ __device__ __forceinline__ void pixel_f64(const AaiKernelParams &kp, double cx, 
     }
 }
 
-// cells that can have non-zero overlap: |i - cx| < hb + 1/2, intersected with the reference's clamped window.
-// Returns true when the image border cut the range (a border pixel: some of its footprint lies outside the image).
+// Cells that can have non-zero overlap: |i - cx| < hb + 1/2, clamped to the image.  The reference's search window
+// (Source.cpp:426-429, search_window() above) always contains this range -- its half width L*sqrt(2)/2 + 1 is at
+// least hb + 1/2 = L(c+s)/2 + 1/2 and it is clamped to the same image bounds -- so intersecting with it is a no-op and
+// the cells it adds all have zero overlap.  Returns true when the image border cut the range (a border pixel: some
+// of its footprint lies outside the image).
 __device__ __forceinline__ bool cell_range(const AaiKernelParams &kp, double cx, double cy, int &ix0, int &ix1,
                                            int &jy0, int &jy1) {
-    int wx0, wx1, wy0, wy1;
-    search_window(kp, cx, cy, wx0, wx1, wy0, wy1);
     const double ext = kp.hb + 0.5 + 1e-9;
     const int bx0 = __double2int_ru(cx - ext), bx1 = __double2int_rd(cx + ext);
     const int by0 = __double2int_ru(cy - ext), by1 = __double2int_rd(cy + ext);
-    ix0 = max(wx0, bx0);
-    ix1 = min(wx1, bx1);
-    jy0 = max(wy0, by0);
-    jy1 = min(wy1, by1);
+    ix0 = max(0, bx0);
+    ix1 = min(kp.mod_w - 1, bx1);
+    jy0 = max(0, by0);
+    jy1 = min(kp.mod_h - 1, by1);
     return bx0 < 0 || by0 < 0 || bx1 > kp.mod_w - 1 || by1 > kp.mod_h - 1;
 }
 

@@ -59,8 +59,11 @@ __device__ __forceinline__ void store_f<uint8_t>(void *row, int idx, float v) {
 
 // IDENT: scale 1, quadrant 0 (expanded pixel (i,j) IS source pixel (i,j)): constant element stride, offsets fold
 // into the load instruction.  Otherwise the general expanded-frame affine map + division by the scale.
+#ifndef AAI_F32_MIN_BLOCKS
+#define AAI_F32_MIN_BLOCKS 3
+#endif
 template <typename TI, typename TO, int NC, bool IDENT>
-__global__ void __launch_bounds__(TILE_W *TILE_H)
+__global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
     overlap_kernel_f32(const __grid_constant__ AaiKernelParams kp) {
     const int x = blockIdx.x * TILE_W + threadIdx.x;
     const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
@@ -95,6 +98,8 @@ __global__ void __launch_bounds__(TILE_W *TILE_H)
         float xlT, xrT;
         aai_chord_h_f32(g, ((float)dj0 - fy) - 0.5f, xlT, xrT);
         constexpr int ESZ = (int)sizeof(TI) * NC;
+        const char *rowp0 = (const char *)kp.src + (int64_t)(jy0 - kp.src_y0) * kp.src_pitch + (int64_t)ix0 * ESZ;
+        const char *rowp = rowp0;
 #pragma unroll 1
         for (int r = 0; r < nrows; ++r) {
             const float ry = (float)(dj0 + r) - fy;
@@ -104,10 +109,9 @@ __global__ void __launch_bounds__(TILE_W *TILE_H)
             float lenL = aai_overlap1_f32(yt[0], yb[0], ey);
             const float ur = -ry * g.sn, vr = ry * g.cs;
             const int j = jy0 + r;
-            const char *rowp = nullptr;
             int exr = 0, eyr = 0;
             if (IDENT) {
-                rowp = (const char *)kp.src + (int64_t)(j - kp.src_y0) * kp.src_pitch + (int64_t)ix0 * ESZ;
+                rowp = rowp0 + (int64_t)r * kp.src_pitch;
             } else {
                 exr = kp.e_axj * j + kp.e_ax0 + kp.e_axi * ix0;
                 eyr = kp.e_ayj * j + kp.e_ay0 + kp.e_ayi * ix0;
