@@ -146,6 +146,10 @@ AaiKernelParams aai_make_kernel_params(const aai_plan &p, const aai_image &src, 
     // 1/cos; near-axis angles (1/sin or 1/cos > 20) use the FP64 kernel
     const double amp = std::fmax(1.0, std::fmax(g.inv_c, g.inv_s));
     f.tau = (float)(4e-6 * amp);
+    f.hk = (float)((1.0 + g.k_cs) / 2);
+    f.hm = (float)(h - g.m);
+    f.y_lf = (float)(h * (s - c));
+    f.y_bt = (float)(h * (s + c));
     const uint64_t max_e = (uint64_t)(p.mod_w > p.mod_h ? p.mod_w : p.mod_h);
     k.f32_ok = (s > 0.0 && c > 0.0 && amp <= 20.0 && max_e * p.scale < 0x100000000ULL) ? 1 : 0;
     k.reach = p.reach;

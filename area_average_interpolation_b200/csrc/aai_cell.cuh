@@ -112,6 +112,11 @@ struct AaiShapeF {
     float inv_c, inv_s;
     float m, thr;
     float tau;  // guard band of the FP32 decisions (distance / edge-parameter units)
+    // per-row quirk events (aai_row_quirk_f32)
+    float hk;    // (1 + c/s)/2
+    float hm;    // h - m: |v0| <= hm  <=>  the whole cell lies inside the top/bottom slab
+    float y_lf;  // h(s-c): y of the footprint's left vertex = top end of the left edge   (relative to the centre)
+    float y_bt;  // h(s+c): y of the bottom vertex = bottom end of the left edge
 };
 
 AAI_HD bool aai_sign_product_positive(float a, float b, float c) {
@@ -136,6 +141,14 @@ AAI_HD void aai_chord_h_f32(const AaiShapeF &g, float ty, float &xl, float &xr) 
     xl = fmaxf(fmaf(ty, g.k_sc, -g.k_hc), fmaf(-ty, g.k_cs, -g.k_hs));
     xr = fminf(fmaf(ty, g.k_sc, g.k_hc), fmaf(-ty, g.k_cs, g.k_hs));
     xr = fmaxf(xr, xl);  // empty chord -> zero length
+}
+// same, also returning where the left / right edge LINES (u = -h / u = +h) cross the grid line
+AAI_HD void aai_chord_h_f32(const AaiShapeF &g, float ty, float &xl, float &xr, float &line_l, float &line_r) {
+    line_l = fmaf(ty, g.k_sc, -g.k_hc);
+    line_r = fmaf(ty, g.k_sc, g.k_hc);
+    xl = fmaxf(line_l, fmaf(-ty, g.k_cs, -g.k_hs));
+    xr = fminf(line_r, fmaf(-ty, g.k_cs, g.k_hs));
+    xr = fmaxf(xr, xl);
 }
 AAI_HD void aai_chord_v_f32(const AaiShapeF &g, float tx, float &yt, float &yb) {
     yt = fmaxf(fmaf(tx, g.k_cs, -g.k_hs), fmaf(-tx, g.k_sc, -g.k_hc));
@@ -258,6 +271,84 @@ AAI_HD AaiF2 aai_cell_area_f32x2(const AaiShapeF &g, AaiF2 u0, AaiF2 v0, AaiF2 l
     out.x = need_x > 0.0f ? (neg_x ? tri.x : pent.x) : area.x;
     out.y = need_y > 0.0f ? (neg_y ? tri.y : pent.y) : area.y;
     return out;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Row formulation of the quirk (what the FP32 kernel runs): exact areas for every cell (Green form, no decision),
+// plus, per row band and per left/right edge line, at most two area CORRECTIONS.
+//
+// A left/right edge line has direction (s,c) (down-right).  In a row band it enters through the band's top at
+// column coordinate z (in cells from the left boundary of cell 0) and leaves at z + s/c.  If that crosses a vertical
+// grid line (floor differs), the line cuts the top-right corner of the first cell kT (leg lx = 1 - frac(z) along the
+// top side, ly = lx*c/s down the right side) and the bottom-left corner of the last cell kB (lx' = frac(z + s/c),
+// ly' = lx'*c/s); cells in between are crossed side to side (trapezoids, exact).  For a corner cut with legs (lx, ly):
+//     reference area - exact area = +1/2 (1 - lx - ly)   if the corner is the only one inside (shape 2),
+//                                   -1/2 (1 - lx - ly)   if it is the only one outside (shape 4).
+// Left edge (footprint to its right): kT is the "inside" case, kB the "outside" case; right edge: the other way round.
+// The correction applies iff no other footprint edge meets the cell:
+//   inside case : both crossing points lie on the edge SEGMENT (their y within [ylo, yhi] of the edge);
+//   outside case: the whole cell lies in the top/bottom slab, |v0| <= h - m.
+// (verified pair by pair against the FP64 slab form and the oracle.)
+// ------------------------------------------------------------------------------------------------------------
+AAI_HD float aai_cell_exact_f32(const AaiShapeF &g, float u0, float v0, float lenT, float lenB, float lenL, float lenR) {
+    const float ca = copysignf(g.half, u0) - u0;
+    const float cb = copysignf(g.half, v0) - v0;
+    const float vx = fmaf(ca, g.cs, cb * g.sn);
+    const float vy = fmaf(cb, g.cs, -ca * g.sn);
+    return fmaf(0.25f, (lenT + lenB) + (lenL + lenR), 0.5f * fmaf(vy, lenT - lenB, vx * (lenL - lenR)));
+}
+AAI_HD AaiF2 aai_cell_exact_f32x2(const AaiShapeF &g, AaiF2 u0, AaiF2 v0, AaiF2 lenT, AaiF2 lenB, AaiF2 lenL,
+                                  AaiF2 lenR) {
+    const AaiF2 ca = aai_sub2(aai_f2(copysignf(g.half, u0.x), copysignf(g.half, u0.y)), u0);
+    const AaiF2 cb = aai_sub2(aai_f2(copysignf(g.half, v0.x), copysignf(g.half, v0.y)), v0);
+    const AaiF2 cs2 = aai_f2(g.cs), sn2 = aai_f2(g.sn);
+    const AaiF2 vx = aai_fma2(ca, cs2, aai_mul2(cb, sn2));
+    const AaiF2 vy = aai_fma2(cb, cs2, aai_mul2(ca, aai_f2(-g.sn)));
+    const AaiF2 sum4 = aai_add2(aai_add2(lenT, lenB), aai_add2(lenL, lenR));
+    const AaiF2 cross = aai_fma2(vy, aai_sub2(lenT, lenB), aai_mul2(vx, aai_sub2(lenL, lenR)));
+    return aai_fma2(aai_f2(0.25f), sum4, aai_mul2(aai_f2(0.5f), cross));
+}
+
+// One edge line in one row band.  LEFT: the left edge (u = -h), else the right edge (u = +h).
+//   z        column coordinate of the line at the band's top (cells from the left boundary of column 0)
+//   yT       y of the band's top, relative to the footprint centre
+//   rx0,vrow v0 of cell k in this row is (rx0 + k)*sin + vrow
+// Outputs: (k_in, d_in) correction for the "corner inside" cell, (k_out, d_out) for the "corner outside" cell;
+// k = -1 when there is none.  `worst` accumulates the smallest decision margin.
+template <bool LEFT>
+AAI_HD void aai_row_quirk_f32(const AaiShapeF &g, float z, float yT, float rx0, float vrow, int &k_in, float &d_in,
+                              int &k_out, float &d_out, float &worst) {
+    const float zB = z + g.k_sc;
+    const float kTf = floorf(z), kBf = floorf(zB);
+    const float fT = z - kTf, fB = zB - kBf;
+    const float lxT = 1.0f - fT;
+    const float dT = fmaf(-lxT, g.hk, 0.5f);  // 1/2 (1 - lx - ly) of the top-right cut in cell kT
+    const float dB = fmaf(-fB, g.hk, 0.5f);   // ... of the bottom-left cut in cell kB
+    const bool cut = kBf > kTf;
+    float val_in, val_out;
+    if (LEFT) {  // edge spans y in [y_lf, y_bt]; top-right cut at kT is the inside case
+        val_in = fminf(yT - g.y_lf, g.y_bt - fmaf(lxT, g.k_cs, yT));
+        val_out = g.hm - fabsf(fmaf(rx0 + kBf, g.sn, vrow));
+        k_in = (int)kTf;
+        k_out = (int)kBf;
+        d_in = dT;
+        d_out = -dB;
+    } else {  // edge spans y in [-y_bt, -y_lf]; bottom-left cut at kB is the inside case
+        const float yB = yT + 1.0f;
+        val_in = fminf(fmaf(-fB, g.k_cs, yB) + g.y_bt, -g.y_lf - yB);
+        val_out = g.hm - fabsf(fmaf(rx0 + kTf, g.sn, vrow));
+        k_in = (int)kBf;
+        k_out = (int)kTf;
+        d_in = dB;
+        d_out = -dT;
+    }
+    // decisions: does the line cross a vertical grid line in this band (corner proximity), are the cuts un-disturbed
+    if (fmaxf(val_in, val_out) > -g.tau) {
+        const float prox = fminf(fminf(fT, lxT), fminf(fB, 1.0f - fB));
+        worst = fminf(worst, fminf(prox, fminf(fabsf(val_in), fabsf(val_out))));
+    }
+    if (!(cut && val_in > 0.0f)) k_in = -1;
+    if (!(cut && val_out > 0.0f)) k_out = -1;
 }
 
 // Stand-alone FP32 form for one pair (tests): (fx, fy) = footprint centre minus the nearest integer lattice point,

@@ -11,10 +11,11 @@
 //   * side lengths |side ∩ footprint| are differences of FADD.SAT (no min/max on the half-rate ALU pipe);
 //   * the kernel is instruction-issue bound, so horizontally adjacent cells are evaluated two at a time on
 //     Blackwell's packed FP32 instructions (FFMA2 / FMUL2 / FADD2 = fma.rn.f32x2, sm_100a);
-//   * the reference's shape-2/4 quirk is decided branch-free (aai_cell.cuh); the smallest decision margin of the
-//     pixel is tracked and, when it falls inside the FP32 guard band, or when the pixel's total overlap is tiny
-//     (border slivers need relative accuracy), the pixel is redone in FP64 (pixel_f64) -- FP32 rounding can never
-//     flip one of the reference's discontinuous decisions.
+//   * every cell gets its exact overlap (Green form, no decision); the reference's shape-2/4 quirk is then applied
+//     as at most two area corrections per left/right edge line and row band (aai_row_quirk_f32 in aai_cell.cuh);
+//     the smallest decision margin of the pixel is tracked and, when it falls inside the FP32 guard band, or when
+//     the image border clips the footprint (border pixels need relative accuracy), the pixel is redone in FP64
+//     (pixel_f64) -- FP32 rounding can never flip one of the reference's discontinuous decisions.
 #include "aai_device.cuh"
 
 #ifndef AAI_MAXN
@@ -95,16 +96,17 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         float yt[MAXN + 1], yb[MAXN + 1];
 #pragma unroll
         for (int k = 0; k <= MAXN; ++k) aai_chord_v_f32(g, rx0 + ((float)k - 0.5f), yt[k], yb[k]);
-        float xlT, xrT;
-        aai_chord_h_f32(g, ((float)dj0 - fy) - 0.5f, xlT, xrT);
+        float xlT, xrT, lineL, lineR;  // chord of the footprint and its left/right edge lines on the row's top grid line
+        aai_chord_h_f32(g, ((float)dj0 - fy) - 0.5f, xlT, xrT, lineL, lineR);
+        const float e0 = rx0 - 0.5f;  // left boundary of column 0
         constexpr int ESZ = (int)sizeof(TI) * NC;
         const char *rowp0 = (const char *)kp.src + (int64_t)(jy0 - kp.src_y0) * kp.src_pitch + (int64_t)ix0 * ESZ;
         const char *rowp = rowp0;
 #pragma unroll 1
         for (int r = 0; r < nrows; ++r) {
             const float ry = (float)(dj0 + r) - fy;
-            float xlB, xrB;
-            aai_chord_h_f32(g, ry + 0.5f, xlB, xrB);
+            float xlB, xrB, lineLB, lineRB;
+            aai_chord_h_f32(g, ry + 0.5f, xlB, xrB, lineLB, lineRB);
             const float ey = ry - 0.5f;
             float lenL = aai_overlap1_f32(yt[0], yb[0], ey);
             const float ur = -ry * g.sn, vr = ry * g.cs;
@@ -136,6 +138,25 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                         acc[ch] = fmaf(LoadF<TI>::get(p + ch * (int)sizeof(TI)), area, acc[ch]);
                 }
             };
+            auto take_dyn = [&](int k, float area) {  // same for a run-time column index (k = -1: nothing)
+                if ((unsigned)k < (unsigned)ncols) {
+                    const char *p;
+                    if (IDENT) {
+                        p = rowp + (int64_t)k * ESZ;
+                    } else {
+                        unsigned sx = (unsigned)(exr + k * kp.e_axi), sy = (unsigned)(eyr + k * kp.e_ayi);
+                        if (kp.scale != 1) {
+                            sx = __umulhi(sx, kp.div_magic);
+                            sy = __umulhi(sy, kp.div_magic);
+                        }
+                        p = (const char *)kp.src + (int64_t)((int)sy - kp.src_y0) * kp.src_pitch + (int64_t)sx * ESZ;
+                    }
+                    sumA += area;
+#pragma unroll
+                    for (int ch = 0; ch < NC; ++ch)
+                        acc[ch] = fmaf(LoadF<TI>::get(p + ch * (int)sizeof(TI)), area, acc[ch]);
+                }
+            };
             // cells two at a time on the packed FP32 pipe (FFMA2/FMUL2/FADD2), a last odd cell on the scalar one
 #pragma unroll
             for (int k = 0; k + 1 < MAXN; k += 2) {
@@ -147,7 +168,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 const AaiF2 lB = aai_f2(aai_overlap1_f32(xlB, xrB, exa), aai_overlap1_f32(xlB, xrB, exb));
                 const AaiF2 rx2 = aai_f2(rxa, rxb);
                 const AaiF2 u0 = aai_fma2(rx2, aai_f2(g.cs), aai_f2(ur)), v0 = aai_fma2(rx2, aai_f2(g.sn), aai_f2(vr));
-                const AaiF2 area = aai_cell_area_f32x2(g, u0, v0, lT, lB, aai_f2(lenL, lenM), aai_f2(lenM, lenR), worst);
+                const AaiF2 area = aai_cell_exact_f32x2(g, u0, v0, lT, lB, aai_f2(lenL, lenM), aai_f2(lenM, lenR));
                 lenL = lenR;
                 take(k, area.x);
                 take(k + 1, area.y);
@@ -160,9 +181,22 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 const float lenT = aai_overlap1_f32(xlT, xrT, ex);
                 const float lenB = aai_overlap1_f32(xlB, xrB, ex);
                 const float u0 = fmaf(rx, g.cs, ur), v0 = fmaf(rx, g.sn, vr);
-                const float area = aai_cell_area_f32(g, u0, v0, lenT, lenB, lenL, lenR, worst);
+                const float area = aai_cell_exact_f32(g, u0, v0, lenT, lenB, lenL, lenR);
                 take(k, area);
             }
+            // the reference's shape-2/4 quirk: at most two corrected cells per left/right edge line and row
+            {
+                int ka, kb;
+                float da, db;
+                aai_row_quirk_f32<true>(g, lineL - e0, ey, rx0, vr, ka, da, kb, db, worst);
+                take_dyn(ka, da);
+                take_dyn(kb, db);
+                aai_row_quirk_f32<false>(g, lineR - e0, ey, rx0, vr, ka, da, kb, db, worst);
+                take_dyn(ka, da);
+                take_dyn(kb, db);
+            }
+            lineL = lineLB;
+            lineR = lineRB;
             xlT = xlB;
             xrT = xrB;
         }

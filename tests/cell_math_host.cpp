@@ -52,6 +52,10 @@ static AaiShapeF make_shape_f(double c, double s, double L) {
     g.inv_c = (float)(1.0 / c); g.inv_s = (float)(1.0 / s);
     g.m = (float)((c + s) / 2); g.thr = (float)(std::fabs(c - s) / 2);
     g.tau = (float)(4e-6 * std::fmax(1.0, std::fmax(1.0 / c, 1.0 / s)));
+    g.hk = (float)((1.0 + c / s) / 2);
+    g.hm = (float)(h - (c + s) / 2);
+    g.y_lf = (float)(h * (s - c));
+    g.y_bt = (float)(h * (s + c));
     return g;
 }
 
@@ -124,4 +128,43 @@ extern "C" void aai_test_pair_areas_f32x2(double c, double s, double L, const do
         out1[k] = a.y;
         flag[k] = worst < g.tau ? 1 : 0;
     }
+}
+
+
+// Per-cell areas of one footprint over an n x n block of cells starting at (i0, j0), evaluated the way the FP32 kernel
+// does it (exact Green areas + per-row quirk events).  out: n*n floats (row-major), returns the decision margin.
+extern "C" float aai_test_footprint_rows_f32(double c, double s, double L, double cx, double cy, int i0, int j0, int n,
+                                             float *out) {
+    const AaiShapeF g = make_shape_f(c, s, L);
+    const double rcx = std::nearbyint(cx), rcy = std::nearbyint(cy);
+    const float fx = (float)(cx - rcx), fy = (float)(cy - rcy);
+    const float rx0 = (float)(i0 - (int)rcx) - fx;
+    const int dj0 = j0 - (int)rcy;
+    float worst = 1.0f;
+    for (int r = 0; r < n; ++r) {
+        const float ry = (float)(dj0 + r) - fy;
+        float xlT, xrT, lineL, lineR, xlB, xrB;
+        aai_chord_h_f32(g, ry - 0.5f, xlT, xrT, lineL, lineR);
+        aai_chord_h_f32(g, ry + 0.5f, xlB, xrB);
+        const float ey = ry - 0.5f, ur = -ry * g.sn, vr = ry * g.cs;
+        for (int k = 0; k < n; ++k) {
+            const float rx = rx0 + (float)k, ex = rx - 0.5f;
+            float ytL, ybL, ytR, ybR;
+            aai_chord_v_f32(g, rx - 0.5f, ytL, ybL);
+            aai_chord_v_f32(g, rx + 0.5f, ytR, ybR);
+            out[r * n + k] = aai_cell_exact_f32(g, fmaf(rx, g.cs, ur), fmaf(rx, g.sn, vr), aai_overlap1_f32(xlT, xrT, ex),
+                                                aai_overlap1_f32(xlB, xrB, ex), aai_overlap1_f32(ytL, ybL, ey),
+                                                aai_overlap1_f32(ytR, ybR, ey));
+        }
+        const float e0 = rx0 - 0.5f;
+        int ka, kb;
+        float da, db;
+        aai_row_quirk_f32<true>(g, lineL - e0, ey, rx0, vr, ka, da, kb, db, worst);
+        if (ka >= 0 && ka < n) out[r * n + ka] += da;
+        if (kb >= 0 && kb < n) out[r * n + kb] += db;
+        aai_row_quirk_f32<false>(g, lineR - e0, ey, rx0, vr, ka, da, kb, db, worst);
+        if (ka >= 0 && ka < n) out[r * n + ka] += da;
+        if (kb >= 0 && kb < n) out[r * n + kb] += db;
+    }
+    return worst;
 }
