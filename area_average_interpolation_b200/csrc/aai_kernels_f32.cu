@@ -102,6 +102,30 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         constexpr int ESZ = (int)sizeof(TI) * NC;
         const char *rowp0 = (const char *)kp.src + (int64_t)(jy0 - kp.src_y0) * kp.src_pitch + (int64_t)ix0 * ESZ;
         const char *rowp = rowp0;
+        // General path: expanded pixel (i,j) -> source pixel is separable (one source coordinate depends on the
+        // column only, the other on the row only; which one is swapped for quadrants 1/3), so the byte offset is
+        // col_off(i) + row_off(j); the column parts are hoisted out of the row loop.
+        const bool swapped = kp.e_axi == 0;
+        auto div_s = [&](int e) -> int64_t {
+            return (int64_t)(kp.scale != 1 ? __umulhi((unsigned)e, kp.div_magic) : (unsigned)e);
+        };
+        auto col_off = [&](int i) -> int64_t {
+            return swapped ? (div_s(kp.e_ayi * i + kp.e_ay0) - kp.src_y0) * kp.src_pitch
+                           : div_s(kp.e_axi * i + kp.e_ax0) * ESZ;
+        };
+        auto row_off = [&](int j) -> int64_t {
+            return swapped ? div_s(kp.e_axj * j + kp.e_ax0) * ESZ
+                           : (div_s(kp.e_ayj * j + kp.e_ay0) - kp.src_y0) * kp.src_pitch;
+        };
+        int64_t coff[MAXN];
+        if (!IDENT) {
+#pragma unroll
+            for (int k = 0; k < MAXN; ++k) coff[k] = col_off(ix0 + min(k, ncols - 1));
+        }
+        // lengths of the cells' top sides inside the footprint: the previous row's bottom sides
+        float lenTop[MAXN];
+#pragma unroll
+        for (int k = 0; k < MAXN; ++k) lenTop[k] = aai_overlap1_f32(xlT, xrT, e0 + (float)k);
 #pragma unroll 1
         for (int r = 0; r < nrows; ++r) {
             const float ry = (float)(dj0 + r) - fy;
@@ -111,27 +135,14 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             float lenL = aai_overlap1_f32(yt[0], yb[0], ey);
             const float ur = -ry * g.sn, vr = ry * g.cs;
             const int j = jy0 + r;
-            int exr = 0, eyr = 0;
-            if (IDENT) {
+            if (IDENT)
                 rowp = rowp0 + (int64_t)r * kp.src_pitch;
-            } else {
-                exr = kp.e_axj * j + kp.e_ax0 + kp.e_axi * ix0;
-                eyr = kp.e_ayj * j + kp.e_ay0 + kp.e_ayi * ix0;
-            }
+            else
+                rowp = (const char *)kp.src + row_off(j);
             // load + accumulate one cell (predicated: columns beyond the footprint box are never read)
             auto take = [&](int k, float area) {
                 if (k < ncols) {
-                    const char *p;
-                    if (IDENT) {
-                        p = rowp + k * ESZ;
-                    } else {
-                        unsigned sx = (unsigned)(exr + k * kp.e_axi), sy = (unsigned)(eyr + k * kp.e_ayi);
-                        if (kp.scale != 1) {
-                            sx = __umulhi(sx, kp.div_magic);
-                            sy = __umulhi(sy, kp.div_magic);
-                        }
-                        p = (const char *)kp.src + (int64_t)((int)sy - kp.src_y0) * kp.src_pitch + (int64_t)sx * ESZ;
-                    }
+                    const char *p = IDENT ? rowp + k * ESZ : rowp + coff[k];
                     sumA += area;
 #pragma unroll
                     for (int ch = 0; ch < NC; ++ch)
@@ -140,17 +151,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             };
             auto take_dyn = [&](int k, float area) {  // same for a run-time column index (k = -1: nothing)
                 if ((unsigned)k < (unsigned)ncols) {
-                    const char *p;
-                    if (IDENT) {
-                        p = rowp + (int64_t)k * ESZ;
-                    } else {
-                        unsigned sx = (unsigned)(exr + k * kp.e_axi), sy = (unsigned)(eyr + k * kp.e_ayi);
-                        if (kp.scale != 1) {
-                            sx = __umulhi(sx, kp.div_magic);
-                            sy = __umulhi(sy, kp.div_magic);
-                        }
-                        p = (const char *)kp.src + (int64_t)((int)sy - kp.src_y0) * kp.src_pitch + (int64_t)sx * ESZ;
-                    }
+                    const char *p = IDENT ? rowp + (int64_t)k * ESZ : rowp + col_off(ix0 + k);
                     sumA += area;
 #pragma unroll
                     for (int ch = 0; ch < NC; ++ch)
@@ -164,8 +165,10 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 const float exa = rxa - 0.5f, exb = rxb - 0.5f;
                 const float lenM = aai_overlap1_f32(yt[k + 1], yb[k + 1], ey);
                 const float lenR = aai_overlap1_f32(yt[k + 2], yb[k + 2], ey);
-                const AaiF2 lT = aai_f2(aai_overlap1_f32(xlT, xrT, exa), aai_overlap1_f32(xlT, xrT, exb));
+                const AaiF2 lT = aai_f2(lenTop[k], lenTop[k + 1]);
                 const AaiF2 lB = aai_f2(aai_overlap1_f32(xlB, xrB, exa), aai_overlap1_f32(xlB, xrB, exb));
+                lenTop[k] = lB.x;
+                lenTop[k + 1] = lB.y;
                 const AaiF2 rx2 = aai_f2(rxa, rxb);
                 const AaiF2 u0 = aai_fma2(rx2, aai_f2(g.cs), aai_f2(ur)), v0 = aai_fma2(rx2, aai_f2(g.sn), aai_f2(vr));
                 const AaiF2 area = aai_cell_exact_f32x2(g, u0, v0, lT, lB, aai_f2(lenL, lenM), aai_f2(lenM, lenR));
@@ -178,8 +181,9 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 const float rx = rx0 + (float)k;
                 const float ex = rx - 0.5f;
                 const float lenR = aai_overlap1_f32(yt[k + 1], yb[k + 1], ey);
-                const float lenT = aai_overlap1_f32(xlT, xrT, ex);
+                const float lenT = lenTop[k];
                 const float lenB = aai_overlap1_f32(xlB, xrB, ex);
+                lenTop[k] = lenB;
                 const float u0 = fmaf(rx, g.cs, ur), v0 = fmaf(rx, g.sn, vr);
                 const float area = aai_cell_exact_f32(g, u0, v0, lenT, lenB, lenL, lenR);
                 take(k, area);
@@ -197,8 +201,6 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             }
             lineL = lineLB;
             lineR = lineRB;
-            xlT = xlB;
-            xrT = xrB;
         }
         // guard band of the quirk decision -> FP64
         redo = worst < g.tau || sumA < 0.25f;
