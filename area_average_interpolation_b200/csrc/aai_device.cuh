@@ -12,8 +12,14 @@
 
 namespace aai_dev {
 
-constexpr int TILE_W = 16;
-constexpr int TILE_H = 16;
+#ifndef AAI_TILE_W
+#define AAI_TILE_W 16
+#endif
+#ifndef AAI_TILE_H
+#define AAI_TILE_H 16
+#endif
+constexpr int TILE_W = AAI_TILE_W;  // canvas pixels per CTA (one thread each); a warp covers 32/TILE_W rows
+constexpr int TILE_H = AAI_TILE_H;
 
 template <typename T>
 struct SrcLoad;
