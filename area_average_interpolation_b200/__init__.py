@@ -96,6 +96,14 @@ def lib() -> C.CDLL:
         L.aai_image_upload.argtypes = [C.POINTER(Image), C.POINTER(Image), C.c_int, C.c_void_p]
         L.aai_image_download.restype = C.c_int
         L.aai_image_download.argtypes = [C.POINTER(Image), C.POINTER(Image), C.c_int, C.c_void_p]
+        L.aai_image_copy_rows.restype = C.c_int
+        L.aai_image_copy_rows.argtypes = [C.POINTER(Image), C.POINTER(Image), C.c_int64, C.c_int64, C.c_int, C.c_void_p]
+        L.aai_ipc_export.restype = C.c_int
+        L.aai_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
+        L.aai_ipc_open.restype = C.c_int
+        L.aai_ipc_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.aai_ipc_close.restype = C.c_int
+        L.aai_ipc_close.argtypes = [C.c_void_p, C.c_int]
         L.aai_run_device.restype = C.c_int
         L.aai_run_device.argtypes = [C.POINTER(Plan), C.c_int, C.c_int, C.POINTER(Image), C.POINTER(Image),
                                      C.c_int64, C.c_int64, C.c_int, C.c_void_p]
@@ -211,6 +219,49 @@ def tensor_image(t, y0: int = 0, height: Optional[int] = None) -> Image:
                  int(y0), rows, dt, ch)
 
 
+def image_alloc(device: int, width: int, height: int, dtype: int, channels: int = 1, y0: int = 0,
+                rows: Optional[int] = None) -> Image:
+    """``aai_image_alloc``: pitched device image (or a band of rows of one)."""
+    img = Image()
+    _check(lib().aai_image_alloc(C.byref(img), int(device), int(width), int(height), int(y0),
+                                 int(height if rows is None else rows), int(dtype), int(channels)))
+    return img
+
+
+def image_free(img: Image, device: int) -> None:
+    _check(lib().aai_image_free(C.byref(img), int(device)))
+
+
+def image_upload(device_img: Image, host_img: Image, device: int = 0, stream: int = 0) -> None:
+    _check(lib().aai_image_upload(C.byref(device_img), C.byref(host_img), int(device), C.c_void_p(stream)))
+
+
+def image_download(host_img: Image, device_img: Image, device: int = 0, stream: int = 0) -> None:
+    _check(lib().aai_image_download(C.byref(host_img), C.byref(device_img), int(device), C.c_void_p(stream)))
+
+
+def image_copy_rows(dst_img: Image, src_img: Image, y0: int, y1: int, device: int = 0, stream: int = 0) -> None:
+    """Device-to-device rows [y0,y1) (a peer device's image goes over NVLink)."""
+    _check(lib().aai_image_copy_rows(C.byref(dst_img), C.byref(src_img), int(y0), int(y1), int(device),
+                                     C.c_void_p(stream)))
+
+
+def ipc_export(device_ptr: int) -> bytes:
+    buf = C.create_string_buffer(64)
+    _check(lib().aai_ipc_export(C.c_void_p(device_ptr), buf))
+    return buf.raw
+
+
+def ipc_open(handle: bytes, device: int) -> int:
+    p = C.c_void_p()
+    _check(lib().aai_ipc_open(handle, int(device), C.byref(p)))
+    return p.value
+
+
+def ipc_close(device_ptr: int, device: int) -> None:
+    _check(lib().aai_ipc_close(C.c_void_p(device_ptr), int(device)))
+
+
 def run_device(plan: Plan, src_img: Image, dst_img: Image, row0: int = 0, row1: Optional[int] = None,
                mode: int = MODE_AREA_AVERAGE, arith: int = ARITH_F64, device: int = 0, stream: int = 0) -> None:
     """``aai_run_device``: enqueue the kernels for canvas rows [row0,row1) on ``stream`` of ``device``."""
@@ -304,6 +355,7 @@ class AreaAverageInterpolation:
 
 __all__ = [
     "AreaAverageInterpolation", "Result", "Plan", "Image", "AaiError", "make_plan", "partition_rows",
-    "band_source_window", "covered_pixels", "device_count", "launch_count", "last_host_timing", "run_device", "run_device_batch",
+    "band_source_window", "covered_pixels", "device_count", "launch_count", "last_host_timing", "run_device", "run_device_batch", "image_alloc", "image_free", "image_upload", "image_download", "image_copy_rows",
+    "ipc_export", "ipc_open", "ipc_close",
     "run_host", "run_host_band", "tensor_image", "status_string", "last_error", "lib", "LIB_PATH",
 ]

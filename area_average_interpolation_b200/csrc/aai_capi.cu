@@ -261,6 +261,48 @@ int aai_image_download(const aai_image *host_img, const aai_image *device_img, i
     return copy_rows(host_img, device_img, cudaMemcpyDeviceToHost, device, stream);
 }
 
+int aai_image_copy_rows(const aai_image *dst, const aai_image *src, int64_t y0, int64_t y1, int device, void *stream) {
+    if (!image_ok(dst) || !image_ok(src) || dst->width != src->width || dst->height != src->height ||
+        dst->dtype != src->dtype || dst->channels != src->channels || y0 < 0 || y1 < y0 || y0 < dst->y0 ||
+        y1 > dst->y0 + dst->rows || y0 < src->y0 || y1 > src->y0 + src->rows) {
+        aai_set_error("aai_image_copy_rows: incompatible images or rows [%lld,%lld) not present", (long long)y0,
+                      (long long)y1);
+        return AAI_ERR_ARGUMENT;
+    }
+    if (y1 == y0) return AAI_OK;
+    AAI_CUDA(cudaSetDevice(device));
+    const size_t row_bytes = (size_t)(src->width * src->channels) * elem_size(src->dtype);
+    AAI_CUDA(cudaMemcpy2DAsync((char *)dst->data + (y0 - dst->y0) * dst->pitch_bytes, (size_t)dst->pitch_bytes,
+                               (const char *)src->data + (y0 - src->y0) * src->pitch_bytes, (size_t)src->pitch_bytes,
+                               row_bytes, (size_t)(y1 - y0), cudaMemcpyDefault, (cudaStream_t)stream));
+    return AAI_OK;
+}
+
+int aai_ipc_export(const void *device_ptr, unsigned char handle[AAI_IPC_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == AAI_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!device_ptr || !handle) return AAI_ERR_ARGUMENT;
+    cudaIpcMemHandle_t h;
+    AAI_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(device_ptr)));
+    std::memcpy(handle, &h, sizeof h);
+    return AAI_OK;
+}
+
+int aai_ipc_open(const unsigned char handle[AAI_IPC_HANDLE_BYTES], int device, void **device_ptr) {
+    if (!handle || !device_ptr) return AAI_ERR_ARGUMENT;
+    AAI_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    AAI_CUDA(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return AAI_OK;
+}
+
+int aai_ipc_close(void *device_ptr, int device) {
+    if (!device_ptr) return AAI_OK;
+    AAI_CUDA(cudaSetDevice(device));
+    AAI_CUDA(cudaIpcCloseMemHandle(device_ptr));
+    return AAI_OK;
+}
+
 int aai_run_device(const aai_plan *plan, int mode, int arith, const aai_image *src, const aai_image *dst,
                    int64_t row0, int64_t row1, int device, void *stream) {
     if (!plan) {

@@ -239,34 +239,79 @@ def our_arm(args, cfg):
     stream = torch.cuda.current_stream().cuda_stream
     shape_tail = (CH,) if CH > 1 else ()
 
+    peer = None
     if cfg["batch"] == 1:
         # one image, canvas row bands
         band = band_for_rank(plan, rank, world)
-        halo_rows = band.src_y1 - band.src_y0
-        host_src = torch.empty((max(halo_rows, 1), W) + shape_tail, dtype=t_dt, pin_memory=True)
-        if halo_rows:
-            synthetic_image(W, H, np_dt, seed, channels=CH, y0=band.src_y0, rows=halo_rows,
-                            out=host_src.numpy()[:halo_rows])
         host_dst = torch.empty((band.rows, plan.dst_w) + shape_tail, dtype=out_dt, pin_memory=True)
-        dev_src = host_src.to(dev)
         dev_dst = torch.empty((band.rows, plan.dst_w) + shape_tail, dtype=out_dt, device=dev)
-        si = aai.tensor_image(dev_src[:halo_rows] if halo_rows else dev_src, y0=band.src_y0, height=H)
         di = aai.tensor_image(dev_dst, y0=band.row0, height=plan.dst_h)
-        hsi = aai.tensor_image(host_src[:halo_rows] if halo_rows else host_src, y0=band.src_y0, height=H)
         hdi = aai.tensor_image(host_dst, y0=band.row0, height=plan.dst_h)
         my_pixels = band.rows * plan.dst_w
         launches_per_step = 1
+        d2h = band.rows * plan.dst_w * CH * host_dst.element_size()
+        if world > 1 and not args.no_peer:
+            # every source row crosses PCIe once (its owner uploads it); halos are pulled over NVLink (CUDA IPC)
+            try:
+                from area_average_interpolation_b200.sharding import PeerSource
+
+                def gather(obj):
+                    out = [None] * world
+                    dist.all_gather_object(out, obj)
+                    return out
+
+                peer = PeerSource(plan, aai._NP_TO_AAI[np_dt], CH, rank, world, local, band, gather)
+            except Exception as exc:  # IPC unavailable: every rank uploads its own halo from the host
+                print(f"[bench] rank {rank}: peer source exchange unavailable ({exc}); uploading halos from host",
+                      file=sys.stderr)
+                peer = None
+            ok = torch.tensor([1 if peer is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0 and peer is not None:
+                peer.close()
+                peer = None
+        if peer is not None:
+            o0, o1 = peer.owned_rows()
+            host_src = torch.empty((o1 - o0, W) + shape_tail, dtype=t_dt, pin_memory=True)
+            synthetic_image(W, H, np_dt, seed, channels=CH, y0=o0, rows=o1 - o0, out=host_src.numpy())
+            hsi = aai.tensor_image(host_src, y0=o0, height=H)
+            si = peer.full
+            resident_bytes = (band.src_y1 - band.src_y0) * W * CH * np_dt.itemsize
+
+            def sync():
+                torch.cuda.current_stream().synchronize()
+                dist.barrier()
+
+            def e2e_step():
+                peer.upload_owned(hsi, stream)
+                sync()                      # every owner's rows are on its device
+                peer.pull_halo(stream)      # NVLink peer copies of the rows this band needs but does not own
+                aai.run_device(plan, si, di, band.row0, band.row1, arith=arith, device=local, stream=stream)
+                aai.image_download(hdi, di, local, stream)
+                sync()                      # peers have finished reading before the next upload overwrites
+
+            e2e_step()  # populates this rank's halo for the device-timed loop
+            h2d = (o1 - o0) * W * CH * np_dt.itemsize
+        else:
+            halo_rows = band.src_y1 - band.src_y0
+            host_src = torch.empty((max(halo_rows, 1), W) + shape_tail, dtype=t_dt, pin_memory=True)
+            if halo_rows:
+                synthetic_image(W, H, np_dt, seed, channels=CH, y0=band.src_y0, rows=halo_rows,
+                                out=host_src.numpy()[:halo_rows])
+            dev_src = host_src.to(dev)
+            si = aai.tensor_image(dev_src[:halo_rows] if halo_rows else dev_src, y0=band.src_y0, height=H)
+            hsi = aai.tensor_image(host_src[:halo_rows] if halo_rows else host_src, y0=band.src_y0, height=H)
+            resident_bytes = dev_src.numel() * dev_src.element_size()
+
+            def e2e_step():
+                aai.run_host_band(plan, hsi, hdi, band.row0, band.row1, arith=arith, device=local, stream=stream,
+                                  synchronize=False)
+
+            h2d = halo_rows * W * CH * np_dt.itemsize
 
         def step():
             aai.run_device(plan, si, di, band.row0, band.row1, arith=arith, device=local, stream=stream)
 
-        def e2e_step():
-            aai.run_host_band(plan, hsi, hdi, band.row0, band.row1, arith=arith, device=local, stream=stream,
-                              synchronize=False)
-
-        h2d = halo_rows * W * CH * np_dt.itemsize
-        d2h = band.rows * plan.dst_w * CH * host_dst.element_size()
-        resident_bytes = dev_src.numel() * dev_src.element_size()
     else:
         # batch of independent images: whole images per rank
         lo, hi = batch_slice(cfg["batch"], rank, world)
@@ -396,7 +441,10 @@ def our_arm(args, cfg):
                                                              else "whole images per rank"),
                    "timing": f"inputs larger than L2 ({resident_bytes / 1e6:.0f} MB resident source per rank)"
                    if resident_bytes > 130e6 else "L2-resident input (source smaller than L2); latency bound",
-                   "covered_pixels": covered},
+                   "covered_pixels": covered,
+                   "e2e_source": ("each source row uploaded once by its owner rank, halos pulled over NVLink "
+                                  "(CUDA IPC peer copies, no NCCL on the data path)" if peer is not None else
+                                  "each rank uploads its band's source halo from pinned host memory (chunk-pipelined)")},
         "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")},
         "e2e": {"value": total_pixels / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d_total,
                 "d2h_bytes_per_step": d2h_total, "ms_per_step": e2e_ms},
@@ -413,6 +461,9 @@ def our_arm(args, cfg):
                       "single thread as the reference ships"}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if peer is not None:
+        barrier()
+        peer.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -428,6 +479,8 @@ def main():
     ap.add_argument("--arith", default="auto", choices=["auto", "f64", "f32"],
                     help="auto: FP32 kernel for float32/8-bit images, FP64 kernel for float64 images")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peer", action="store_true",
+                    help="N>1: every rank uploads its whole halo from the host instead of NVLink peer copies")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

@@ -137,6 +137,19 @@ int aai_image_free(aai_image *img, int device);
 int aai_image_upload(const aai_image *device_img, const aai_image *host_img, int device, void *stream);
 int aai_image_download(const aai_image *host_img, const aai_image *device_img, int device, void *stream);
 
+/* Copies rows [y0,y1) of a device image into another device image of the same shape (same or PEER device: with
+ * peer access enabled the copy goes over NVLink).  Both must hold those rows.  Asynchronous on `stream`. */
+int aai_image_copy_rows(const aai_image *dst_device_img, const aai_image *src_device_img, int64_t y0, int64_t y1,
+                        int device, void *stream);
+
+/* Cross-process sharing of a device image for one-process-per-GPU launches (CUDA IPC): the owner exports the
+ * allocation that `device_ptr` points to (it must be the base of an aai_image_alloc / cudaMalloc allocation), a peer
+ * process opens it on its own device and can then read it with aai_image_copy_rows (NVLink peer copy, no NCCL). */
+#define AAI_IPC_HANDLE_BYTES 64
+int aai_ipc_export(const void *device_ptr, unsigned char handle[AAI_IPC_HANDLE_BYTES]);
+int aai_ipc_open(const unsigned char handle[AAI_IPC_HANDLE_BYTES], int device, void **device_ptr);
+int aai_ipc_close(void *device_ptr, int device);
+
 /* ---- the hot path --------------------------------------------------------------------------------------- */
 
 /* Main loop of the reference (Source.cpp:411-579 / 866-907) for canvas rows [row0,row1) on one device.

@@ -291,6 +291,28 @@ def test_batch_of_slices_is_one_launch_and_matches_per_image_runs(aai, oracle):
     assert torch.equal(out2, ref[order])
 
 
+def test_device_image_helpers_roundtrip(aai):
+    """aai_image_alloc / upload / copy_rows / download: pitched device images and row-range copies."""
+    rng = np.random.default_rng(4)
+    host = rng.uniform(0, 1, size=(37, 53)).astype(np.float32)
+    himg = aai._host_image(host)
+    a = aai.image_alloc(0, 53, 37, aai.F32)
+    b = aai.image_alloc(0, 53, 37, aai.F32)
+    assert a.pitch_bytes % 512 == 0
+    aai.image_upload(a, himg)
+    aai.image_copy_rows(b, a, 5, 30)
+    back = np.zeros_like(host)
+    aai.image_download(aai._host_image(back), b)
+    import torch
+
+    torch.cuda.synchronize()
+    assert np.array_equal(back[5:30], host[5:30])
+    with pytest.raises(aai.AaiError):
+        aai.image_copy_rows(b, a, 30, 40)
+    aai.image_free(a, 0)
+    aai.image_free(b, 0)
+
+
 def test_argument_errors_are_reported_not_crashed(aai):
     import torch
 
