@@ -27,6 +27,10 @@ using namespace aai_dev;
 namespace {
 
 constexpr int MAXN = AAI_MAXN;
+#ifndef AAI_ROW_UNROLL
+#define AAI_ROW_UNROLL 1
+#endif
+constexpr int kRowUnroll = AAI_ROW_UNROLL;
 
 template <typename T>
 struct LoadF;
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         float lenTop[MAXN];
 #pragma unroll
         for (int k = 0; k < MAXN; ++k) lenTop[k] = aai_overlap1_f32(xlT, xrT, e0 + (float)k);
-#pragma unroll 1
+#pragma unroll kRowUnroll
         for (int r = 0; r < nrows; ++r) {
             const float ry = (float)(dj0 + r) - fy;
             float xlB, xrB, lineLB, lineRB;
