@@ -249,8 +249,12 @@ static int copy_rows(const aai_image *dst, const aai_image *src, cudaMemcpyKind 
     const size_t row_bytes = (size_t)(band->width * band->channels) * elem_size(band->dtype);
     const char *s = (const char *)src->data + (kind == cudaMemcpyHostToDevice ? (band->y0 - src->y0) * src->pitch_bytes : 0);
     char *d = (char *)dst->data + (kind == cudaMemcpyDeviceToHost ? (band->y0 - dst->y0) * dst->pitch_bytes : 0);
-    AAI_CUDA(cudaMemcpy2DAsync(d, (size_t)dst->pitch_bytes, s, (size_t)src->pitch_bytes, row_bytes,
-                               (size_t)band->rows, kind, (cudaStream_t)stream));
+    if (dst->pitch_bytes == src->pitch_bytes)  // same pitch: one linear copy (faster DMA than a strided 2-D copy)
+        AAI_CUDA(cudaMemcpyAsync(d, s, (size_t)src->pitch_bytes * (size_t)(band->rows - 1) + row_bytes, kind,
+                                 (cudaStream_t)stream));
+    else
+        AAI_CUDA(cudaMemcpy2DAsync(d, (size_t)dst->pitch_bytes, s, (size_t)src->pitch_bytes, row_bytes,
+                                   (size_t)band->rows, kind, (cudaStream_t)stream));
     return AAI_OK;
 }
 
@@ -272,9 +276,14 @@ int aai_image_copy_rows(const aai_image *dst, const aai_image *src, int64_t y0, 
     if (y1 == y0) return AAI_OK;
     AAI_CUDA(cudaSetDevice(device));
     const size_t row_bytes = (size_t)(src->width * src->channels) * elem_size(src->dtype);
-    AAI_CUDA(cudaMemcpy2DAsync((char *)dst->data + (y0 - dst->y0) * dst->pitch_bytes, (size_t)dst->pitch_bytes,
-                               (const char *)src->data + (y0 - src->y0) * src->pitch_bytes, (size_t)src->pitch_bytes,
-                               row_bytes, (size_t)(y1 - y0), cudaMemcpyDefault, (cudaStream_t)stream));
+    char *d = (char *)dst->data + (y0 - dst->y0) * dst->pitch_bytes;
+    const char *s = (const char *)src->data + (y0 - src->y0) * src->pitch_bytes;
+    if ((size_t)dst->pitch_bytes == (size_t)src->pitch_bytes)  // same pitch: one linear copy (padding included)
+        AAI_CUDA(cudaMemcpyAsync(d, s, (size_t)src->pitch_bytes * (size_t)(y1 - y0), cudaMemcpyDefault,
+                                 (cudaStream_t)stream));
+    else
+        AAI_CUDA(cudaMemcpy2DAsync(d, (size_t)dst->pitch_bytes, s, (size_t)src->pitch_bytes, row_bytes,
+                                   (size_t)(y1 - y0), cudaMemcpyDefault, (cudaStream_t)stream));
     return AAI_OK;
 }
 

@@ -282,13 +282,29 @@ def our_arm(args, cfg):
                 torch.cuda.current_stream().synchronize()
                 dist.barrier()
 
+            phases = os.environ.get("AAI_BENCH_PHASES")
+
             def e2e_step():
+                t = [time.perf_counter()]
                 peer.upload_owned(hsi, stream)
+                if phases:
+                    torch.cuda.current_stream().synchronize(); t.append(time.perf_counter())
                 sync()                      # every owner's rows are on its device
-                peer.pull_halo(stream)      # NVLink peer copies of the rows this band needs but does not own
+                if phases:
+                    t.append(time.perf_counter())
+                moved = peer.pull_halo(stream)      # NVLink peer copies of the rows this band needs but does not own
+                if phases:
+                    torch.cuda.current_stream().synchronize(); t.append(time.perf_counter())
                 aai.run_device(plan, si, di, band.row0, band.row1, arith=arith, device=local, stream=stream)
                 aai.image_download(hdi, di, local, stream)
+                if phases:
+                    torch.cuda.current_stream().synchronize(); t.append(time.perf_counter())
                 sync()                      # peers have finished reading before the next upload overwrites
+                if phases:
+                    t.append(time.perf_counter())
+                    print(f"[phases] rank {rank}: upload {1e3*(t[1]-t[0]):.2f} barrier {1e3*(t[2]-t[1]):.2f} pull "
+                          f"{1e3*(t[3]-t[2]):.2f} ({moved/1e6:.0f} MB) kernel+d2h {1e3*(t[4]-t[3]):.2f} barrier "
+                          f"{1e3*(t[5]-t[4]):.2f} ms", file=sys.stderr)
 
             e2e_step()  # populates this rank's halo for the device-timed loop
             h2d = (o1 - o0) * W * CH * np_dt.itemsize
