@@ -21,7 +21,7 @@ AAI_OK = 0
 ERR_RESOLUTION_XY, ERR_RESOLUTION_NONPOS, ERR_NO_ROWS, ERR_NO_COLUMNS = 1, 2, 3, 4
 ERR_ANGLE, ERR_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE = 5, 6, 7, 8
 F64, F32, U8 = 0, 1, 2
-MODE_AREA_AVERAGE, MODE_FAST = 1, 2
+MODE_AREA_AVERAGE, MODE_FAST, MODE_AREA_AVERAGE_EXACT = 1, 2, 3
 ARITH_F64, ARITH_F32 = 0, 1
 
 _NP_TO_AAI = {np.dtype(np.float64): F64, np.dtype(np.float32): F32, np.dtype(np.uint8): U8}
@@ -104,6 +104,8 @@ def lib() -> C.CDLL:
         L.aai_ipc_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
         L.aai_ipc_close.restype = C.c_int
         L.aai_ipc_close.argtypes = [C.c_void_p, C.c_int]
+        L.aai_expand_device.restype = C.c_int
+        L.aai_expand_device.argtypes = [C.POINTER(Plan), C.POINTER(Image), C.POINTER(Image), C.c_int, C.c_void_p]
         L.aai_run_device.restype = C.c_int
         L.aai_run_device.argtypes = [C.POINTER(Plan), C.c_int, C.c_int, C.POINTER(Image), C.POINTER(Image),
                                      C.c_int64, C.c_int64, C.c_int, C.c_void_p]
@@ -262,6 +264,11 @@ def ipc_close(device_ptr: int, device: int) -> None:
     _check(lib().aai_ipc_close(C.c_void_p(device_ptr), int(device)))
 
 
+def expand_device(plan: Plan, src_img: Image, dst_mod_img: Image, device: int = 0, stream: int = 0) -> None:
+    """``aai_expand_device``: the reference's expanded + quadrant-rotated source ``modSrc`` (Source.cpp:157-172)."""
+    _check(lib().aai_expand_device(C.byref(plan), C.byref(src_img), C.byref(dst_mod_img), int(device), C.c_void_p(stream)))
+
+
 def run_device(plan: Plan, src_img: Image, dst_img: Image, row0: int = 0, row1: Optional[int] = None,
                mode: int = MODE_AREA_AVERAGE, arith: int = ARITH_F64, device: int = 0, stream: int = 0) -> None:
     """``aai_run_device``: enqueue the kernels for canvas rows [row0,row1) on ``stream`` of ``device``."""
@@ -352,10 +359,16 @@ class AreaAverageInterpolation:
                                      dstIsocenter=(0.0, 0.0)) -> Result:
         return self._run(MODE_FAST, src, srcResolution, dstResolution, srcIsocenter, rotationAngle, dstIsocenter)
 
+    def exactAreaAverageInterpolation(self, src, srcResolution, dstResolution, srcIsocenter, rotationAngle,
+                                      dstIsocenter=(0.0, 0.0)) -> Result:
+        """Not in the reference: geometrically exact overlap areas, without the shape-2/4 quirk."""
+        return self._run(MODE_AREA_AVERAGE_EXACT, src, srcResolution, dstResolution, srcIsocenter, rotationAngle,
+                         dstIsocenter)
+
 
 __all__ = [
     "AreaAverageInterpolation", "Result", "Plan", "Image", "AaiError", "make_plan", "partition_rows",
-    "band_source_window", "covered_pixels", "device_count", "launch_count", "last_host_timing", "run_device", "run_device_batch", "image_alloc", "image_free", "image_upload", "image_download", "image_copy_rows",
+    "band_source_window", "covered_pixels", "device_count", "launch_count", "last_host_timing", "run_device", "run_device_batch", "expand_device", "image_alloc", "image_free", "image_upload", "image_download", "image_copy_rows",
     "ipc_export", "ipc_open", "ipc_close",
     "run_host", "run_host_band", "tensor_image", "status_string", "last_error", "lib", "LIB_PATH",
 ]

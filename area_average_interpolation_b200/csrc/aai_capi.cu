@@ -130,28 +130,13 @@ AaiKernelParams aai_make_kernel_params(const aai_plan &p, const aai_image &src, 
     g.inv_s = 1.0 / s;
     g.m = (c + s) / 2;
     g.thr = std::fabs(c - s) / 2;
-    AaiShapeF &f = k.shapef;
-    f.cs = (float)c;
-    f.sn = (float)s;
-    f.half = (float)h;
-    f.k_sc = (float)g.k_sc;
-    f.k_hc = (float)g.k_hc;
-    f.k_cs = (float)g.k_cs;
-    f.k_hs = (float)g.k_hs;
-    f.inv_c = (float)g.inv_c;
-    f.inv_s = (float)g.inv_s;
-    f.m = (float)g.m;
-    f.thr = (float)g.thr;
-    // guard band of the FP32 shape decisions: ~8x the rounding error of the FP32 margins, which scales with 1/sin,
-    // 1/cos; near-axis angles (1/sin or 1/cos > 20) use the FP64 kernel
+    // FP32 constants incl. the guard band of the FP32 shape decisions; near-axis angles (1/sin or 1/cos > 20) use the
+    // FP64 kernel
+    k.shapef = aai_make_shape_f(c, s, p.side);
     const double amp = std::fmax(1.0, std::fmax(g.inv_c, g.inv_s));
-    f.tau = (float)(4e-6 * amp);
-    f.hk = (float)((1.0 + g.k_cs) / 2);
-    f.hm = (float)(h - g.m);
-    f.y_lf = (float)(h * (s - c));
-    f.y_bt = (float)(h * (s + c));
     const uint64_t max_e = (uint64_t)(p.mod_w > p.mod_h ? p.mod_w : p.mod_h);
     k.f32_ok = (s > 0.0 && c > 0.0 && amp <= 20.0 && max_e * p.scale < 0x100000000ULL) ? 1 : 0;
+    k.quirk = 1;
     k.reach = p.reach;
     k.hb = h * (c + s);
     k.mod_w = (int32_t)p.mod_w;
@@ -325,8 +310,8 @@ int aai_run_device(const aai_plan *plan, int mode, int arith, const aai_image *s
                       (long long)plan->src_w, (long long)plan->src_h, (long long)plan->dst_w, (long long)plan->dst_h);
         return AAI_ERR_ARGUMENT;
     }
-    if (mode != AAI_MODE_AREA_AVERAGE && mode != AAI_MODE_FAST) {
-        aai_set_error("aai_run_device: interpolation mode must be 1 or 2");
+    if (mode != AAI_MODE_AREA_AVERAGE && mode != AAI_MODE_FAST && mode != AAI_MODE_AREA_AVERAGE_EXACT) {
+        aai_set_error("aai_run_device: interpolation mode must be 1, 2 or 3");
         return AAI_ERR_ARGUMENT;
     }
     if (arith != AAI_ARITH_F64 && arith != AAI_ARITH_F32) {
@@ -346,7 +331,8 @@ int aai_run_device(const aai_plan *plan, int mode, int arith, const aai_image *s
         return AAI_ERR_ARGUMENT;
     }
     AAI_CUDA(cudaSetDevice(device));
-    const AaiKernelParams kp = aai_make_kernel_params(*plan, *src, *dst, row0, row1);
+    AaiKernelParams kp = aai_make_kernel_params(*plan, *src, *dst, row0, row1);
+    kp.quirk = mode == AAI_MODE_AREA_AVERAGE_EXACT ? 0 : 1;
     int e;
     if (mode == AAI_MODE_FAST)
         e = aai_launch_fast(kp, src->dtype, dst->dtype, stream);
@@ -375,6 +361,34 @@ static int check_host_images(const char *who, const aai_plan *plan, const aai_im
         aai_set_error("%s: whole host images expected", who);
         return AAI_ERR_ARGUMENT;
     }
+    return AAI_OK;
+}
+
+int aai_expand_device(const aai_plan *plan, const aai_image *src, const aai_image *dst_mod, int device, void *stream) {
+    if (!plan) {
+        aai_set_error("aai_expand_device: null plan");
+        return AAI_ERR_ARGUMENT;
+    }
+    if (plan->status != AAI_OK) return plan->status;
+    if (!image_ok(src) || !image_ok(dst_mod) || src->width != plan->src_w || src->height != plan->src_h ||
+        src->y0 != 0 || src->rows != src->height || dst_mod->width != plan->mod_w || dst_mod->height != plan->mod_h ||
+        dst_mod->y0 != 0 || dst_mod->rows != dst_mod->height || src->dtype != dst_mod->dtype ||
+        src->channels != dst_mod->channels) {
+        aai_set_error("aai_expand_device: need a whole source image and a whole %lld x %lld image of the same type",
+                      (long long)plan->mod_w, (long long)plan->mod_h);
+        return AAI_ERR_ARGUMENT;
+    }
+    AAI_CUDA(cudaSetDevice(device));
+    // the kernel-parameter builder takes canvas-shaped destinations; only the source view and the index map are used
+    aai_image canvas = *dst_mod;
+    canvas.width = plan->dst_w;
+    canvas.height = plan->dst_h;
+    AaiKernelParams kp = aai_make_kernel_params(*plan, *src, canvas, 0, 0);
+    kp.dst = dst_mod->data;
+    kp.dst_pitch = dst_mod->pitch_bytes;
+    const int e = aai_launch_expand(kp, (int)elem_size(src->dtype), stream);
+    g_launches.fetch_add(1);
+    if (e != (int)cudaSuccess) return cuda_fail((cudaError_t)e, "expand kernel launch");
     return AAI_OK;
 }
 

@@ -52,7 +52,7 @@ AAI_HD double aai_overlap1(double lo, double hi, double r) {
 // given the lengths of the four cell sides inside the footprint.  Reference-compatible (includes the shape 2/4
 // leg quirk of Source.cpp:1055-1062).
 AAI_HD double aai_cell_area(const AaiShape &g, double rx, double ry, double lenT, double lenB, double lenL,
-                            double lenR) {
+                            double lenR, bool quirk = true) {
     // footprint-local coordinates of the cell centre; nearest footprint vertex V in cell-local coordinates
     const double u0 = rx * g.cs - ry * g.sn;
     const double v0 = rx * g.sn + ry * g.cs;
@@ -63,7 +63,7 @@ AAI_HD double aai_cell_area(const AaiShape &g, double rx, double ry, double lenT
     // Reference quirk.  a = signed distance of the cell centre inside the nearest left/right edge.
     const double a = g.half - fabs(u0);
     const double aa = fabs(a);
-    if (aa > g.thr && aa < g.m) {  // that edge's line isolates exactly one cell corner
+    if (quirk && aa > g.thr && aa < g.m) {  // that edge's line isolates exactly one cell corner
         const double sv = copysign(1.0, v0), su = copysign(1.0, u0);
         // the left/right edge is the ray from W = sv*V along -(s,c); the cell is [-1/2,1/2]^2 (slab test)
         const double wx = sv * vx, wy = sv * vy;
@@ -117,7 +117,51 @@ struct AaiShapeF {
     float hm;    // h - m: |v0| <= hm  <=>  the whole cell lies inside the top/bottom slab
     float y_lf;  // h(s-c): y of the footprint's left vertex = top end of the left edge   (relative to the centre)
     float y_bt;  // h(s+c): y of the bottom vertex = bottom end of the left edge
+    // per-edge quirk events (aai_edge_quirk_f32): "major" axis = the grid axis the left/right edges mostly run along
+    // (y when sin <= cos, else x), "minor" axis = the other one
+    float hb;    // h(c+s): half extent of the footprint's bounding box
+    float he;    // h|c-s|
+    float ik;    // max(s,c)/min(s,c): advance along the major axis per unit of the minor axis
+    float hq;    // (1 + min/max)/2
+    float smin, smax;  // min(s,c), max(s,c)
+    float area_total;  // L^2: total overlap of a footprint that lies inside the image (exact areas)
+    int steep;   // 1: sin <= cos (major axis = y, the edges cross vertical grid lines rarely)
+    int ncross;  // floor(L min(s,c)) + 1: most minor-axis grid lines one left/right edge can cross
 };
+
+// image-wide FP32 constants from the FP64 plan values (host side; shared by the C ABI and the CPU tests)
+inline AaiShapeF aai_make_shape_f(double c, double s, double L) {
+    AaiShapeF g;
+    const double h = L / 2;
+    g.cs = (float)c;
+    g.sn = (float)s;
+    g.half = (float)h;
+    g.k_sc = (float)(s / c);
+    g.k_hc = (float)(h / c);
+    g.k_cs = (float)(c / s);
+    g.k_hs = (float)(h / s);
+    g.inv_c = (float)(1.0 / c);
+    g.inv_s = (float)(1.0 / s);
+    g.m = (float)((c + s) / 2);
+    g.thr = (float)(fabs(c - s) / 2);
+    // guard band of the FP32 decisions: ~8x the rounding error of the FP32 margins, which scales with 1/sin, 1/cos
+    g.tau = (float)(4e-6 * fmax(1.0, fmax(1.0 / c, 1.0 / s)));
+    g.hk = (float)((1.0 + c / s) / 2);
+    g.hm = (float)(h - (c + s) / 2);
+    g.y_lf = (float)(h * (s - c));
+    g.y_bt = (float)(h * (s + c));
+    const double mn = s < c ? s : c, mx = s < c ? c : s;
+    g.hb = (float)(h * (c + s));
+    g.he = (float)(h * fabs(c - s));
+    g.ik = (float)(mx / mn);
+    g.hq = (float)((1.0 + mn / mx) / 2);
+    g.smin = (float)mn;
+    g.smax = (float)mx;
+    g.area_total = (float)(L * L);
+    g.steep = s <= c ? 1 : 0;
+    g.ncross = (int)floor(L * mn) + 1;
+    return g;
+}
 
 AAI_HD bool aai_sign_product_positive(float a, float b, float c) {
 #if defined(__CUDA_ARCH__)
@@ -349,6 +393,70 @@ AAI_HD void aai_row_quirk_f32(const AaiShapeF &g, float z, float yT, float rx0, 
     }
     if (!(cut && val_in > 0.0f)) k_in = -1;
     if (!(cut && val_out > 0.0f)) k_out = -1;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Edge formulation of the quirk (what the FP32 kernel runs now): the corrected cells of the row formulation above
+// are exactly the cells in which a left/right edge changes from "advancing along its major axis" to "stepping over a
+// minor-axis grid line" -- one pair of cells per minor-axis grid line the edge SEGMENT crosses, at most
+// floor(L min(s,c)) + 1 of them -- so they are enumerated per edge instead of being searched for in every row.
+//
+// Axes: the left/right edges have direction (s,c).  Major axis = y if s <= c ("steep"), else x; minor = the other.
+// Along the edge both coordinates increase; kappa = min/max is the minor advance per unit of major advance.  At a
+// crossing of the minor grid line Q, at major coordinate p* = (cell index Mi) + f:
+//   "before" cell (minor index mi,   major index Mi): the edge entered through its lower major side and leaves through
+//            the grid line: legs f and f*kappa                     -> 1/2 (1 - lx - ly) = 1/2 - f hq
+//   "after"  cell (minor index mi+1, major index Mi): legs (1-f) and (1-f)*kappa     -> 1/2 - (1-f) hq
+// (steep: before = top-right cut, after = bottom-left cut; shallow: the other way round).  In (major, minor)
+// coordinates relative to the footprint centre the edges are, with D = h(c+s), E = h|c-s|:
+//   ALPHA (left edge if steep, right edge if shallow): major in [-E, D], minor in [-D, -E]; the before cell has its
+//         cut corner INSIDE the footprint (reference shape 2, +), the after cell OUTSIDE (shape 4, -);
+//   BETA  (right edge if steep, left edge if shallow): major in [-D, E], minor in [E, D]; before = outside, after =
+//         inside.
+// Validity as in the row formulation: inside case <=> both crossing points of the cell lie on the edge segment;
+// outside case <=> the whole cell lies in the top/bottom slab, |v0| <= h - m, v0 = minor*min(s,c) + major*max(s,c).
+//   g0m, g0M : coordinate of grid line 0 on the minor / major axis (left boundary of column 0 resp. top of row 0)
+//   n        : which crossing of this edge (0 = first minor grid line after the edge's start)
+// Outputs: (mi, Mi) = before cell (the after cell is (mi+1, Mi)); d_before / d_after = signed area corrections, 0
+// when the cell is not a quirk cell.  `worst` accumulates the smallest decision margin.
+// ------------------------------------------------------------------------------------------------------------
+template <bool ALPHA>
+AAI_HD void aai_edge_quirk_f32(const AaiShapeF &g, float g0m, float g0M, int n, int &mi, int &Mi, float &d_before,
+                               float &d_after, float &worst) {
+    const float qA = ALPHA ? -g.hb : g.he, qB = ALPHA ? -g.he : g.hb;
+    const float pA = ALPHA ? -g.he : -g.hb;
+    const float span = g.hb + g.he;  // pB - pA
+    const float icf = ceilf(qA - g0m) + (float)n;
+    const float Q = g0m + icf;
+    const float dq = Q - qA;
+    const float ex = fminf(dq, qB - Q);  // the grid line really crosses the segment
+    const float along = dq * g.ik;       // major-axis distance from the edge's start to the crossing
+    const float rel = (pA - g0M) + along;
+    const float Mf = floorf(rel);
+    const float f = rel - Mf, f1 = 1.0f - f;
+    const float d_b = fmaf(-f, g.hq, 0.5f), d_a = fmaf(-f1, g.hq, 0.5f);
+    const float pc = (g0M + Mf) + 0.5f;  // major coordinate of the two cells' centres
+    float val_in, val_out;
+    if (ALPHA) {
+        val_in = fminf(along - f, span - along);
+        val_out = g.hm - fabsf(fmaf(Q + 0.5f, g.smin, pc * g.smax));
+    } else {
+        val_in = fminf((span - along) - f1, along);
+        val_out = g.hm - fabsf(fmaf(Q - 0.5f, g.smin, pc * g.smax));
+    }
+    val_in = fminf(val_in, ex);
+    val_out = fminf(val_out, ex);
+    if (fmaxf(val_in, val_out) > -g.tau)
+        worst = fminf(worst, fminf(fminf(f, f1), fminf(fabsf(val_in), fabsf(val_out))));
+    mi = (int)icf - 1;
+    Mi = (int)Mf;
+    if (ALPHA) {
+        d_before = val_in > 0.0f ? d_b : 0.0f;
+        d_after = val_out > 0.0f ? -d_a : 0.0f;
+    } else {
+        d_before = val_out > 0.0f ? -d_b : 0.0f;
+        d_after = val_in > 0.0f ? d_a : 0.0f;
+    }
 }
 
 // Stand-alone FP32 form for one pair (tests): (fx, fy) = footprint centre minus the nearest integer lattice point,

@@ -122,7 +122,7 @@ __device__ __forceinline__ void pixel_f64(const AaiKernelParams &kp, double cx, 
             const double lenR = aai_overlap1(yt, yb, ry);
             const double lenT = aai_overlap1(xlT, xrT, rx);
             const double lenB = aai_overlap1(xlB, xrB, rx);
-            const double area = aai_cell_area(g, rx, ry, lenT, lenB, lenL, lenR);
+            const double area = aai_cell_area(g, rx, ry, lenT, lenB, lenL, lenR, kp.quirk != 0);
             lenL = lenR;
             if (area != 0.0) {
                 int sx, sy;

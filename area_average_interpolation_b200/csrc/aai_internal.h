@@ -15,6 +15,7 @@ struct AaiKernelParams {
     AaiShape shape;   // cos/sin, h = L/2 and the derived footprint constants (aai_cell.cuh)
     AaiShapeF shapef; // the same in FP32 (+ guard band) for the FP32 kernel
     int32_t f32_ok;   // FP32 kernel admissible (angle not within ~3 degrees of an axis)
+    int32_t quirk;    // 1: reproduce the reference's shape-2/4 leg quirk (default), 0: geometrically exact areas
     double reach;     // L*sqrt(2)/2 (search window, 426-429)
     double hb;        // h*(c+s): half extent of the footprint's axis-aligned bounding box
     int32_t mod_w, mod_h, dst_w, dst_h;
@@ -44,6 +45,7 @@ AaiKernelParams aai_make_kernel_params(const aai_plan &plan, const aai_image &sr
 int aai_launch_overlap(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_separable(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_fast(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
+int aai_launch_expand(const AaiKernelParams &kp, int elem_bytes, void *stream);
 // aai_kernels_sep.cu: TMA-staged separable kernel; returns cudaErrorNotSupported when its fast path does not apply
 int aai_launch_separable_tma(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);
 // aai_kernels_f32.cu, one translation unit per maximum cell count per axis

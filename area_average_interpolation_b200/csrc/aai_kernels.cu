@@ -128,6 +128,21 @@ __global__ void __launch_bounds__(TILE_W *TILE_H) fast_kernel(const __grid_const
     for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, count > 0 ? acc[ch] / (double)count : 0.0);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Stand-alone expansion + quadrant pre-rotation (Source.cpp:157-172): modSrc[my][mx] = src[sy][sx].
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) expand_kernel(const __grid_constant__ AaiKernelParams kp) {
+    const int mx = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int my = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (mx >= kp.mod_w || my >= kp.mod_h) return;
+    int sx, sy;
+    mod_to_src(kp, mx, my, sx, sy);
+    const T *srow = (const T *)((const char *)kp.src + (int64_t)(sy - kp.src_y0) * kp.src_pitch);
+    T *drow = (T *)((char *)kp.dst + (int64_t)my * kp.dst_pitch);
+    for (int ch = 0; ch < kp.channels; ++ch) drow[mx * kp.channels + ch] = srow[sx * kp.channels + ch];
+}
+
 enum KernelKind { K_OVERLAP, K_SEPARABLE, K_FAST };
 
 template <typename TI, typename TO, int NC>
@@ -193,6 +208,19 @@ int aai_launch_separable(const AaiKernelParams &kp, int arith, int src_dtype, in
     if (e != (int)cudaErrorNotSupported) return e;
     return (int)launch_any(K_SEPARABLE, kp, src_dtype, dst_dtype, (cudaStream_t)stream);
 }
+int aai_launch_expand(const AaiKernelParams &kp, int elem_bytes, void *stream) {
+    if (kp.mod_w <= 0 || kp.mod_h <= 0) return (int)cudaSuccess;
+    const dim3 grid((kp.mod_w + 63) / 64, (kp.mod_h + 3) / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (elem_bytes) {
+        case 1: expand_kernel<uint8_t><<<grid, 256, 0, st>>>(kp); break;
+        case 4: expand_kernel<float><<<grid, 256, 0, st>>>(kp); break;
+        case 8: expand_kernel<double><<<grid, 256, 0, st>>>(kp); break;
+        default: return (int)cudaErrorInvalidValue;
+    }
+    return (int)cudaGetLastError();
+}
+
 int aai_launch_fast(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream) {
     return (int)launch_any(K_FAST, kp, src_dtype, dst_dtype, (cudaStream_t)stream);
 }

@@ -11,8 +11,10 @@
 //   * side lengths |side ∩ footprint| are differences of FADD.SAT (no min/max on the half-rate ALU pipe);
 //   * the kernel is instruction-issue bound, so horizontally adjacent cells are evaluated two at a time on
 //     Blackwell's packed FP32 instructions (FFMA2 / FMUL2 / FADD2 = fma.rn.f32x2, sm_100a);
-//   * every cell gets its exact overlap (Green form, no decision); the reference's shape-2/4 quirk is then applied
-//     as at most two area corrections per left/right edge line and row band (aai_row_quirk_f32 in aai_cell.cuh);
+//   * every cell gets its exact overlap (Green form, no decision), so the total area of a footprint inside the image
+//     is L^2 and is not accumulated; the reference's shape-2/4 quirk is then applied as one pair of corrected cells
+//     per minor-axis grid line that a left/right footprint edge crosses (aai_edge_quirk_f32 in aai_cell.cuh: at most
+//     2 (floor(L min(s,c)) + 1) events per canvas pixel instead of a search in every row);
 //     the smallest decision margin of the pixel is tracked and, when it falls inside the FP32 guard band, or when
 //     the image border clips the footprint (border pixels need relative accuracy), the pixel is redone in FP64
 //     (pixel_f64) -- FP32 rounding can never flip one of the reference's discontinuous decisions.
@@ -100,8 +102,9 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         float yt[MAXN + 1], yb[MAXN + 1];
 #pragma unroll
         for (int k = 0; k <= MAXN; ++k) aai_chord_v_f32(g, rx0 + ((float)k - 0.5f), yt[k], yb[k]);
-        float xlT, xrT, lineL, lineR;  // chord of the footprint and its left/right edge lines on the row's top grid line
-        aai_chord_h_f32(g, ((float)dj0 - fy) - 0.5f, xlT, xrT, lineL, lineR);
+        float xlT, xrT;  // chord of the footprint on the row's top grid line
+        const float t0 = ((float)dj0 - fy) - 0.5f;  // top of row 0
+        aai_chord_h_f32(g, t0, xlT, xrT);
         const float e0 = rx0 - 0.5f;  // left boundary of column 0
         constexpr int ESZ = (int)sizeof(TI) * NC;
         const char *rowp0 = (const char *)kp.src + (int64_t)(jy0 - kp.src_y0) * kp.src_pitch + (int64_t)ix0 * ESZ;
@@ -133,8 +136,8 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
 #pragma unroll kRowUnroll
         for (int r = 0; r < nrows; ++r) {
             const float ry = (float)(dj0 + r) - fy;
-            float xlB, xrB, lineLB, lineRB;
-            aai_chord_h_f32(g, ry + 0.5f, xlB, xrB, lineLB, lineRB);
+            float xlB, xrB;
+            aai_chord_h_f32(g, ry + 0.5f, xlB, xrB);
             const float ey = ry - 0.5f;
             float lenL = aai_overlap1_f32(yt[0], yb[0], ey);
             const float ur = -ry * g.sn, vr = ry * g.cs;
@@ -147,16 +150,6 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             auto take = [&](int k, float area) {
                 if (k < ncols) {
                     const char *p = IDENT ? rowp + k * ESZ : rowp + coff[k];
-                    sumA += area;
-#pragma unroll
-                    for (int ch = 0; ch < NC; ++ch)
-                        acc[ch] = fmaf(LoadF<TI>::get(p + ch * (int)sizeof(TI)), area, acc[ch]);
-                }
-            };
-            auto take_dyn = [&](int k, float area) {  // same for a run-time column index (k = -1: nothing)
-                if ((unsigned)k < (unsigned)ncols) {
-                    const char *p = IDENT ? rowp + (int64_t)k * ESZ : rowp + col_off(ix0 + k);
-                    sumA += area;
 #pragma unroll
                     for (int ch = 0; ch < NC; ++ch)
                         acc[ch] = fmaf(LoadF<TI>::get(p + ch * (int)sizeof(TI)), area, acc[ch]);
@@ -192,19 +185,34 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 const float area = aai_cell_exact_f32(g, u0, v0, lenT, lenB, lenL, lenR);
                 take(k, area);
             }
-            // the reference's shape-2/4 quirk: at most two corrected cells per left/right edge line and row
-            {
-                int ka, kb;
-                float da, db;
-                aai_row_quirk_f32<true>(g, lineL - e0, ey, rx0, vr, ka, da, kb, db, worst);
-                take_dyn(ka, da);
-                take_dyn(kb, db);
-                aai_row_quirk_f32<false>(g, lineR - e0, ey, rx0, vr, ka, da, kb, db, worst);
-                take_dyn(ka, da);
-                take_dyn(kb, db);
+        }
+        // Total overlap: the exact areas of a footprint inside the image add up to L^2 (border pixels never get here).
+        sumA = g.area_total;
+        // The reference's shape-2/4 quirk: one pair of corrected cells per minor-axis grid line crossed by a left/right
+        // edge.
+        if (kp.quirk) {
+            const float g0m = g.steep ? e0 : t0, g0M = g.steep ? t0 : e0;
+            auto fix = [&](int mi, int Mi, float d) {  // cell (minor index, major index) += d
+                const int k = g.steep ? mi : Mi, r = g.steep ? Mi : mi;
+                if (d != 0.0f && (unsigned)k < (unsigned)ncols && (unsigned)r < (unsigned)nrows) {
+                    const char *p = IDENT ? rowp0 + (int64_t)r * kp.src_pitch + (int64_t)k * ESZ
+                                          : (const char *)kp.src + row_off(jy0 + r) + col_off(ix0 + k);
+                    sumA += d;
+#pragma unroll
+                    for (int ch = 0; ch < NC; ++ch)
+                        acc[ch] = fmaf(LoadF<TI>::get(p + ch * (int)sizeof(TI)), d, acc[ch]);
+                }
+            };
+            for (int q = 0; q < g.ncross; ++q) {
+                int mi, Mi;
+                float db, da;
+                aai_edge_quirk_f32<true>(g, g0m, g0M, q, mi, Mi, db, da, worst);
+                fix(mi, Mi, db);
+                fix(mi + 1, Mi, da);
+                aai_edge_quirk_f32<false>(g, g0m, g0M, q, mi, Mi, db, da, worst);
+                fix(mi, Mi, db);
+                fix(mi + 1, Mi, da);
             }
-            lineL = lineLB;
-            lineR = lineRB;
         }
         // guard band of the quirk decision -> FP64
         redo = worst < g.tau || sumA < 0.25f;

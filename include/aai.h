@@ -53,7 +53,11 @@ enum { AAI_F64 = 0, AAI_F32 = 1, AAI_U8 = 2 };
 /* Interpolation mode = the reference's `interpolationMode` user setting (Source.cpp:1534). */
 enum {
     AAI_MODE_AREA_AVERAGE = 1, /* areaAverageInterpolation      (Source.cpp:55)  -- the north-star path */
-    AAI_MODE_FAST = 2          /* fastAreaAverageInterpolation  (Source.cpp:584) */
+    AAI_MODE_FAST = 2,         /* fastAreaAverageInterpolation  (Source.cpp:584) */
+    /* beyond the reference: geometrically exact overlap areas, i.e. area averaging WITHOUT the
+     * reference's shape-2/4 leg quirk (Source.cpp:1055-1062); opt-in, never the default, checked against its own
+     * exact polygon-clipping oracle */
+    AAI_MODE_AREA_AVERAGE_EXACT = 3
 };
 
 /* Arithmetic of the overlap kernel. */
@@ -149,6 +153,12 @@ int aai_image_copy_rows(const aai_image *dst_device_img, const aai_image *src_de
 int aai_ipc_export(const void *device_ptr, unsigned char handle[AAI_IPC_HANDLE_BYTES]);
 int aai_ipc_open(const unsigned char handle[AAI_IPC_HANDLE_BYTES], int device, void **device_ptr);
 int aai_ipc_close(void *device_ptr, int device);
+
+/* Row f3 of SURVEY 8f: the reference's expansion + quadrant pre-rotation (Source.cpp:157-172) as a stand-alone device
+ * op, for callers that want `modSrc` itself: dst_mod (plan->mod_w x plan->mod_h, same dtype / channels as src) receives
+ * the source replicated `scale` times and rotated quadrant*90 degrees clockwise.  (The resampling kernels never
+ * materialise it; they index the source through the same map.) */
+int aai_expand_device(const aai_plan *plan, const aai_image *src, const aai_image *dst_mod, int device, void *stream);
 
 /* ---- the hot path --------------------------------------------------------------------------------------- */
 

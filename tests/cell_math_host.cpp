@@ -44,20 +44,7 @@ extern "C" void aai_test_image_f64(double c, double s, double L, double offIx, d
         }
 }
 
-static AaiShapeF make_shape_f(double c, double s, double L) {
-    AaiShapeF g;
-    const double h = L / 2;
-    g.cs = (float)c; g.sn = (float)s; g.half = (float)h;
-    g.k_sc = (float)(s / c); g.k_hc = (float)(h / c); g.k_cs = (float)(c / s); g.k_hs = (float)(h / s);
-    g.inv_c = (float)(1.0 / c); g.inv_s = (float)(1.0 / s);
-    g.m = (float)((c + s) / 2); g.thr = (float)(std::fabs(c - s) / 2);
-    g.tau = (float)(4e-6 * std::fmax(1.0, std::fmax(1.0 / c, 1.0 / s)));
-    g.hk = (float)((1.0 + c / s) / 2);
-    g.hm = (float)(h - (c + s) / 2);
-    g.y_lf = (float)(h * (s - c));
-    g.y_bt = (float)(h * (s + c));
-    return g;
-}
+static AaiShapeF make_shape_f(double c, double s, double L) { return aai_make_shape_f(c, s, L); }
 
 // FP32 pair areas + the "uncertain" flag (1 = the kernel would redo this pixel in FP64)
 extern "C" void aai_test_pair_areas_f32(double c, double s, double L, const double *cx, const double *cy, const int *i,
@@ -166,5 +153,56 @@ extern "C" float aai_test_footprint_rows_f32(double c, double s, double L, doubl
         if (ka >= 0 && ka < n) out[r * n + ka] += da;
         if (kb >= 0 && kb < n) out[r * n + kb] += db;
     }
+    return worst;
+}
+
+
+// Same block of cells evaluated the way the FP32 kernel does it NOW: exact Green areas + per-edge quirk events
+// (aai_edge_quirk_f32).  out: n*n floats (row-major); *total = L^2 + sum of the corrections (the kernel's sumA);
+// returns the decision margin.
+extern "C" float aai_test_footprint_edges_f32(double c, double s, double L, double cx, double cy, int i0, int j0, int n,
+                                              float *out, float *total) {
+    const AaiShapeF g = make_shape_f(c, s, L);
+    const double rcx = std::nearbyint(cx), rcy = std::nearbyint(cy);
+    const float fx = (float)(cx - rcx), fy = (float)(cy - rcy);
+    const float rx0 = (float)(i0 - (int)rcx) - fx;
+    const int dj0 = j0 - (int)rcy;
+    for (int r = 0; r < n; ++r) {
+        const float ry = (float)(dj0 + r) - fy;
+        float xlT, xrT, xlB, xrB;
+        aai_chord_h_f32(g, ry - 0.5f, xlT, xrT);
+        aai_chord_h_f32(g, ry + 0.5f, xlB, xrB);
+        const float ey = ry - 0.5f, ur = -ry * g.sn, vr = ry * g.cs;
+        for (int k = 0; k < n; ++k) {
+            const float rx = rx0 + (float)k, ex = rx - 0.5f;
+            float ytL, ybL, ytR, ybR;
+            aai_chord_v_f32(g, rx - 0.5f, ytL, ybL);
+            aai_chord_v_f32(g, rx + 0.5f, ytR, ybR);
+            out[r * n + k] = aai_cell_exact_f32(g, fmaf(rx, g.cs, ur), fmaf(rx, g.sn, vr), aai_overlap1_f32(xlT, xrT, ex),
+                                                aai_overlap1_f32(xlB, xrB, ex), aai_overlap1_f32(ytL, ybL, ey),
+                                                aai_overlap1_f32(ytR, ybR, ey));
+        }
+    }
+    const float e0 = rx0 - 0.5f, t0 = ((float)dj0 - fy) - 0.5f;
+    const float g0m = g.steep ? e0 : t0, g0M = g.steep ? t0 : e0;
+    float worst = 1.0f, sum = g.area_total;
+    auto apply = [&](int mi, int Mi, float d) {
+        const int k = g.steep ? mi : Mi, r = g.steep ? Mi : mi;
+        if (d != 0.0f && k >= 0 && k < n && r >= 0 && r < n) {
+            out[r * n + k] += d;
+            sum += d;
+        }
+    };
+    for (int q = 0; q < g.ncross; ++q) {
+        int mi, Mi;
+        float db, da;
+        aai_edge_quirk_f32<true>(g, g0m, g0M, q, mi, Mi, db, da, worst);
+        apply(mi, Mi, db);
+        apply(mi + 1, Mi, da);
+        aai_edge_quirk_f32<false>(g, g0m, g0M, q, mi, Mi, db, da, worst);
+        apply(mi, Mi, db);
+        apply(mi + 1, Mi, da);
+    }
+    *total = sum;
     return worst;
 }

@@ -23,6 +23,8 @@ def cellmath(built):
     lib.aai_test_image_f32.argtypes = [C.c_double] * 9 + [C.c_int] * 4 + [C.c_void_p] * 3
     lib.aai_test_footprint_rows_f32.argtypes = [C.c_double] * 5 + [C.c_int] * 3 + [C.c_void_p]
     lib.aai_test_footprint_rows_f32.restype = C.c_float
+    lib.aai_test_footprint_edges_f32.argtypes = [C.c_double] * 5 + [C.c_int] * 3 + [C.c_void_p] * 2
+    lib.aai_test_footprint_edges_f32.restype = C.c_float
     lib.aai_test_pair_areas_f32x2.argtypes = [C.c_double] * 3 + [C.c_void_p] * 7 + [C.c_longlong]
     return lib
 
@@ -182,3 +184,40 @@ def test_packed_two_cell_form_equals_scalar_form(cellmath):
     cellmath.aai_test_pair_areas_f32(c, s, side, cx.ctypes.data, cy.ctypes.data, i.ctypes.data, j.ctypes.data,
                                      f0.ctypes.data, f1.ctypes.data, n)
     assert np.array_equal(a0, f0)  # lane .x of the packed form is the scalar form, operation by operation
+
+
+@pytest.mark.parametrize("theta,side", [(17.3, 2.7027027), (30.0, 2.7027027), (45.0, 1.7647059), (61.0, 2.0),
+                                        (5.0, 3.3), (85.0, 1.5), (73.0, 3.9), (40.0, 5.1), (52.0, 4.4), (3.5, 1.42)])
+def test_edge_formulation_of_the_quirk_matches_the_per_cell_form(cellmath, theta, side):
+    """What the FP32 kernel runs: exact areas for every cell + one pair of corrected cells per minor-axis grid line
+    that a left/right edge crosses (aai_edge_quirk_f32), total area = L^2 + corrections.  Must reproduce, cell by cell,
+    the FP64 per-cell form (which is checked against the oracle above)."""
+    rng = np.random.default_rng(int(theta * 10) + 3)
+    c, s = np.cos(np.radians(theta)), np.sin(np.radians(theta))
+    n = int(np.floor(side * (c + s) + 1)) + 2
+    tau = 4e-6 * max(1.0, 1.0 / c, 1.0 / s)
+    flagged = 0
+    trials = 3000
+    corrected = 0
+    for _ in range(trials):
+        cx, cy = rng.uniform(100, 116, 2)
+        i0 = int(np.ceil(cx - (side / 2 * (c + s) + 0.5)))
+        j0 = int(np.ceil(cy - (side / 2 * (c + s) + 0.5)))
+        got = np.zeros(n * n, dtype=np.float32)
+        total = np.zeros(1, dtype=np.float32)
+        worst = cellmath.aai_test_footprint_edges_f32(c, s, side, cx, cy, i0, j0, n, got.ctypes.data, total.ctypes.data)
+        ii, jj = np.meshgrid(np.arange(i0, i0 + n), np.arange(j0, j0 + n))
+        i = ii.ravel().astype(np.int32)
+        j = jj.ravel().astype(np.int32)
+        want = np.zeros(n * n)
+        cxa, cya = np.full(n * n, cx), np.full(n * n, cy)
+        cellmath.aai_test_pair_areas(c, s, side, cxa.ctypes.data, cya.ctypes.data, i.ctypes.data, j.ctypes.data,
+                                     want.ctypes.data, n * n)
+        if worst < tau:
+            flagged += 1  # the kernel redoes this pixel in FP64
+        else:
+            assert np.abs(got - want).max() < 5e-6, (cx, cy)
+            assert abs(float(total[0]) - want.sum()) < 2e-5
+            corrected += abs(want.sum() - side * side) > 1e-3
+    assert flagged < 0.01 * trials
+    assert corrected > 0.3 * min(1.0, side * min(c, s)) * trials  # the quirk really fires

@@ -356,10 +356,56 @@ def test_argument_errors_are_reported_not_crashed(aai):
     assert ei.value.status == aai.ERR_ARGUMENT
     dst = torch.zeros(plan.dst_h, plan.dst_w, dtype=torch.float32, device="cuda")
     with pytest.raises(aai.AaiError):
-        aai.run_device(plan, aai.tensor_image(src), aai.tensor_image(dst), mode=3)
+        aai.run_device(plan, aai.tensor_image(src), aai.tensor_image(dst), mode=4)
     # a source band that misses rows the canvas band needs is refused
     with pytest.raises(aai.AaiError):
         aai.run_device(plan, aai.tensor_image(src[:8].contiguous(), y0=0, height=64), aai.tensor_image(dst))
+
+
+# ---- rows f3 / f4 of SURVEY 8f ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("ratio,angle", [(0.37, 17.3), (1.7, 117.0), (0.9, 200.0), (2.3, 305.5), (0.5, 0.0)])
+def test_expand_device_equals_replicate_and_rot90(aai, ratio, angle):
+    """Row f3: modSrc (Source.cpp:157-172) = the source replicated `scale` times, rotated quadrant*90 deg clockwise."""
+    import torch
+
+    rng = np.random.default_rng(9)
+    for dtype, shape in [(np.float32, (37, 53)), (np.uint8, (37, 53, 3)), (np.float64, (20, 31))]:
+        host = (rng.uniform(0, 255, size=shape)).astype(dtype)
+        h, w = shape[:2]
+        plan = aai.make_plan(w, h, 1.0, ratio, (w / 2.0, h / 2.0), angle)
+        src = torch.from_numpy(host).cuda()
+        mod = torch.zeros((plan.mod_h, plan.mod_w) + shape[2:], dtype=src.dtype, device="cuda")
+        before = aai.launch_count()
+        aai.expand_device(plan, aai.tensor_image(src), aai.tensor_image(mod),
+                          stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert aai.launch_count() == before + 1
+        want = np.repeat(np.repeat(host, plan.scale, axis=0), plan.scale, axis=1)
+        want = np.rot90(want, k=-plan.quadrant, axes=(0, 1))  # k*90 degrees clockwise
+        assert want.shape == tuple(mod.shape)
+        assert np.array_equal(mod.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("w,h,ratio,angle,iso", SWEEP[:10])
+def test_exact_mode_matches_its_clipping_checker(aai, oracle, w, h, ratio, angle, iso):
+    """Row f4 (opt-in, not the reference's arithmetic): areas without the shape-2/4 quirk, against Sutherland-Hodgman
+    clipping + shoelace (oracle mode 3), FP64 and FP32 kernels."""
+    rng = np.random.default_rng(w * 17 + h)
+    src = rng.uniform(0.0, 4096.0, size=(h, w))
+    st, want, wiso = oracle.run(src, 1.0, ratio, iso, angle, mode=3)
+    assert st == 0
+    op = aai.AreaAverageInterpolation()
+    r = op.exactAreaAverageInterpolation(src, 1.0, ratio, iso, angle)
+    assert r.ok and r.dst.shape == want.shape and r.dst_isocenter == wiso
+    err = rel_err(r.dst, want)
+    assert err.max() <= TOL_F64_REL, (float(err.max()), int((err > TOL_F64_REL).sum()))
+    op32 = aai.AreaAverageInterpolation(arith=aai.ARITH_F32, out_dtype=np.float32)
+    r32 = op32.exactAreaAverageInterpolation(src.astype(np.float32), 1.0, ratio, iso, angle)
+    st, want32, _ = oracle.run(src.astype(np.float32), 1.0, ratio, iso, angle, mode=3)
+    err = np.abs(r32.dst.astype(np.float64) - want32) / np.maximum(np.abs(want32), 1e-30)
+    err[want32 == 0] = np.abs(r32.dst[want32 == 0])
+    assert err.max() <= TOL_F32_REL, (float(err.max()), int((err > TOL_F32_REL).sum()))
 
 
 # ---- properties (size independent) + full-size configurations -------------------------------------------------------

@@ -73,3 +73,31 @@ def test_oracle_against_compiled_reference_sweep(port):
         assert ok and st == 0
         assert got.shape == want.shape and giso == wiso
         assert np.array_equal(got, want), (w, h, ratio, angle, iso, mode)
+
+
+def test_exact_mode_checker_properties(port):
+    """Row f4's own checker (mode 3: Sutherland-Hodgman clip + shoelace, NOT the reference's algorithm): interior
+    footprints have total area L^2, axis-aligned angles equal the reference mode bit for bit in area, and on rotated
+    inputs it differs from the reference exactly where the shape-2/4 quirk fires."""
+    rng = np.random.default_rng(5)
+    src = rng.uniform(0, 4096, size=(96, 96))
+    p = port.plan(96, 96, 1.0, 0.37, (48.0, 48.0), 17.3)
+    st, exact, _, area = port.run(src, 1.0, 0.37, (48.0, 48.0), 17.3, mode=3, want_area=True)
+    st1, quirk, _, area1 = port.run(src, 1.0, 0.37, (48.0, 48.0), 17.3, mode=1, want_area=True)
+    assert st == 0 and st1 == 0
+    L2 = p["side"] ** 2
+    full = area > 0.99 * L2
+    interior = full.copy()  # erode by one pixel: footprints well away from the image border
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            interior &= np.roll(np.roll(full, dy, axis=0), dx, axis=1)
+    interior[[0, -1], :] = False
+    interior[:, [0, -1]] = False
+    assert interior.mean() > 0.4
+    assert np.abs(area[interior] - L2).max() <= 1e-12 * L2
+    assert np.abs(area1[interior] - L2).max() > 1e-3        # the reference's areas do not add up to L^2
+    assert (np.abs(exact - quirk) > 1e-6).mean() > 0.3      # and its values differ on rotated inputs
+    # axis aligned: no corner cuts -> same result up to summation rounding
+    st, e0, _ = port.run(src, 1.0, 0.5, (48.0, 48.0), 90.0, mode=3)
+    st1, q0, _ = port.run(src, 1.0, 0.5, (48.0, 48.0), 90.0, mode=1)
+    assert np.abs(e0 - q0).max() <= 1e-10
