@@ -446,8 +446,10 @@ AAI_HD void aai_edge_quirk_f32(const AaiShapeF &g, float g0m, float g0M, int n, 
     }
     val_in = fminf(val_in, ex);
     val_out = fminf(val_out, ex);
-    if (fmaxf(val_in, val_out) > -g.tau)
-        worst = fminf(worst, fminf(fminf(f, f1), fminf(fabsf(val_in), fabsf(val_out))));
+    // Decision margins.  A crossing within the guard band of a lattice corner (f ~ 0 or 1) may be assigned to the wrong
+    // pair of cells, so it is flagged whatever the validity of the cells FP32 happened to pick.
+    if (ex > -g.tau) worst = fminf(worst, fminf(f, f1));
+    if (fmaxf(val_in, val_out) > -g.tau) worst = fminf(worst, fminf(fabsf(val_in), fabsf(val_out)));
     mi = (int)icf - 1;
     Mi = (int)Mf;
     if (ALPHA) {

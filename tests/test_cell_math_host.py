@@ -221,3 +221,21 @@ def test_edge_formulation_of_the_quirk_matches_the_per_cell_form(cellmath, theta
             corrected += abs(want.sum() - side * side) > 1e-3
     assert flagged < 0.01 * trials
     assert corrected > 0.3 * min(1.0, side * min(c, s)) * trials  # the quirk really fires
+
+
+def test_edge_crossings_next_to_a_lattice_corner_are_flagged(cellmath):
+    """Five footprints of the config-4 canvas (16384^2, 17.3 deg) whose right edge crosses a vertical grid line within
+    1e-8 of a lattice corner: FP32 assigns the crossing to the wrong row, so the guard band must send them to FP64."""
+    theta, side = 17.3, 1 / 0.37
+    c, s = np.cos(np.radians(theta)), np.sin(np.radians(theta))
+    n = int(np.floor(side * (c + s) + 1)) + 2
+    tau = 4e-6 * max(1.0, 1.0 / c, 1.0 / s)
+    for cx, cy in [(2974.930087200926, 6437.0038590545555), (1111.0160516152882, 10986.27985894395),
+                   (10639.07378538135, 8740.46522064712), (6007.979929102068, 12085.16388258702),
+                   (14312.099825776248, 15698.092180559619)]:
+        i0 = int(np.ceil(cx - (side / 2 * (c + s) + 0.5)))
+        j0 = int(np.ceil(cy - (side / 2 * (c + s) + 0.5)))
+        got = np.zeros(n * n, dtype=np.float32)
+        total = np.zeros(1, dtype=np.float32)
+        worst = cellmath.aai_test_footprint_edges_f32(c, s, side, cx, cy, i0, j0, n, got.ctypes.data, total.ctypes.data)
+        assert worst < tau

@@ -18,3 +18,11 @@ idx = torch.nonzero(rel > 5e-6)
 # border distance proxy: use sumA via area image: run with src=ones in f64 gives 1 where covered; need sumA: approximate by comparing constant image? skip
 for (y, x) in idx[:20].tolist():
     print(y, x, "f64", o64[y, x].item(), "f32", o32[y, x].item(), "rel", rel[y, x].item(), "neighbors covered", ones[max(0,y-1):y+2, max(0,x-1):x+2].sum().item())
+print("total bad", idx.shape[0])
+c, s, L = plan.cos_t, plan.sin_t, plan.side
+for (y, x) in idx[:40].tolist():
+    u = ((x + plan.off_ix) * L - plan.iso_x) + plan.off_x
+    v = ((y + plan.off_iy) * L - plan.iso_y) + plan.off_y
+    cx = (u * c + v * s) + plan.iso_x
+    cy = (-u * s + v * c) + plan.iso_y
+    print("PIX", y, x, repr(cx), repr(cy))
