@@ -116,6 +116,16 @@ AaiKernelParams aai_make_kernel_params(const aai_plan &p, const aai_image &src, 
     k.off_x = p.off_x;
     k.off_y = p.off_y;
     const double c = p.cos_t, s = p.sin_t, h = p.side / 2;
+    {
+        const double u0 = (p.off_ix * p.side - p.iso_x) + p.off_x, v0 = (p.off_iy * p.side - p.iso_y) + p.off_y;
+        k.aff_x0 = (u0 * c + v0 * s) + p.iso_x;
+        k.aff_y0 = (-u0 * s + v0 * c) + p.iso_y;
+        k.aff_xx = p.side * c;
+        k.aff_xy = p.side * s;
+        k.aff_yx = -p.side * s;
+        k.aff_yy = p.side * c;
+        k.ext32 = (float)(h * (c + s) + 0.5 + 2e-6);
+    }
     AaiShape &g = k.shape;
     g.cs = c;
     g.sn = s;

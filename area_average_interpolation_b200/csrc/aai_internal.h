@@ -12,6 +12,9 @@
 struct AaiKernelParams {
     // canvas-pixel centre expression of Source.cpp:212-219
     double side, off_ix, off_iy, iso_x, iso_y, off_x, off_y;
+    // the same centre as an affine map of the canvas pixel (x, y): cx = aff_x0 + x aff_xx + y aff_xy, cy likewise
+    double aff_x0, aff_xx, aff_xy, aff_y0, aff_yx, aff_yy;
+    float ext32;      // hb + 1/2 + 2e-6: half extent of the cell range in the FP32 kernel
     AaiShape shape;   // cos/sin, h = L/2 and the derived footprint constants (aai_cell.cuh)
     AaiShapeF shapef; // the same in FP32 (+ guard band) for the FP32 kernel
     int32_t f32_ok;   // FP32 kernel admissible (angle not within ~3 degrees of an axis)

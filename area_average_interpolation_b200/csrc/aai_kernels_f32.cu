@@ -67,7 +67,7 @@ __device__ __forceinline__ void store_f<uint8_t>(void *row, int idx, float v) {
 // IDENT: scale 1, quadrant 0 (expanded pixel (i,j) IS source pixel (i,j)): constant element stride, offsets fold
 // into the load instruction.  Otherwise the general expanded-frame affine map + division by the scale.
 #ifndef AAI_F32_MIN_BLOCKS
-#define AAI_F32_MIN_BLOCKS 3
+#define AAI_F32_MIN_BLOCKS (AAI_MAXN <= 5 ? 3 : 2)
 #endif
 template <typename TI, typename TO, int NC, bool IDENT>
 __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
@@ -75,10 +75,19 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
     const int x = blockIdx.x * TILE_W + threadIdx.x;
     const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
     if (x >= kp.dst_w || y >= kp.row1) return;
-    double cx, cy;
-    pixel_centre(kp, x, y, cx, cy);
-    int ix0, ix1, jy0, jy1;
-    const bool border = cell_range(kp, cx, cy, ix0, ix1, jy0, jy1);
+    // Footprint centre from the affine form of Source.cpp:212-219 (two FP64 FMAs per coordinate; within ~1e-12 of
+    // the reference's own expression, pixel_centre(), which the FP64 redo path below evaluates), split into the nearest
+    // lattice point and an FP32 fraction.
+    const double cx = fma((double)x, kp.aff_xx, fma((double)y, kp.aff_xy, kp.aff_x0));
+    const double cy = fma((double)x, kp.aff_yx, fma((double)y, kp.aff_yy, kp.aff_y0));
+    const int irx = __double2int_rn(cx), iry = __double2int_rn(cy);
+    const float fx = (float)(cx - (double)irx), fy = (float)(cy - (double)iry);
+    // cells that can have non-zero overlap (|i - cx| < hb + 1/2, FP32 with a safety margin: the cells it may add have
+    // exactly zero area), clamped to the image; border = some of the footprint's box lies outside the image
+    const int bx0 = irx + __float2int_ru(fx - kp.ext32), bx1 = irx + __float2int_rd(fx + kp.ext32);
+    const int by0 = iry + __float2int_ru(fy - kp.ext32), by1 = iry + __float2int_rd(fy + kp.ext32);
+    const int ix0 = max(0, bx0), ix1 = min(kp.mod_w - 1, bx1), jy0 = max(0, by0), jy1 = min(kp.mod_h - 1, by1);
+    const bool border = bx0 < 0 || by0 < 0 || bx1 > kp.mod_w - 1 || by1 > kp.mod_h - 1;
     const int ncols = ix1 - ix0 + 1, nrows = jy1 - jy0 + 1;
     char *drow = (char *)kp.dst + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
     if (ncols <= 0 || nrows <= 0) {  // footprint bounding box misses the image: the reference writes 0 (577)
@@ -95,10 +104,8 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
     bool redo = border || ncols > MAXN || nrows > MAXN;  // (the MAXN test cannot fire for the MAXN the host picked)
     if (!redo) {
         const AaiShapeF &g = kp.shapef;
-        const double rcx = rint(cx), rcy = rint(cy);
-        const float fx = (float)(cx - rcx), fy = (float)(cy - rcy);
-        const int dj0 = jy0 - (int)rcy;
-        const float rx0 = (float)(ix0 - (int)rcx) - fx;
+        const int dj0 = jy0 - iry;
+        const float rx0 = (float)(ix0 - irx) - fx;
         float yt[MAXN + 1], yb[MAXN + 1];
 #pragma unroll
         for (int k = 0; k <= MAXN; ++k) aai_chord_v_f32(g, rx0 + ((float)k - 0.5f), yt[k], yb[k]);
@@ -116,40 +123,67 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         auto div_s = [&](int e) -> int64_t {
             return (int64_t)(kp.scale != 1 ? __umulhi((unsigned)e, kp.div_magic) : (unsigned)e);
         };
-        auto col_off = [&](int i) -> int64_t {
-            return swapped ? (div_s(kp.e_ayi * i + kp.e_ay0) - kp.src_y0) * kp.src_pitch
-                           : div_s(kp.e_axi * i + kp.e_ax0) * ESZ;
+        // column part as a 32-bit source index (row or column of the source) times a 64-bit stride
+        const int64_t cstride = swapped ? kp.src_pitch : (int64_t)ESZ;
+        auto col_idx = [&](int i) -> int {
+            return swapped ? (int)div_s(kp.e_ayi * i + kp.e_ay0) - kp.src_y0 : (int)div_s(kp.e_axi * i + kp.e_ax0);
         };
+        auto col_off = [&](int i) -> int64_t { return (int64_t)col_idx(i) * cstride; };
         auto row_off = [&](int j) -> int64_t {
             return swapped ? div_s(kp.e_axj * j + kp.e_ax0) * ESZ
                            : (div_s(kp.e_ayj * j + kp.e_ay0) - kp.src_y0) * kp.src_pitch;
         };
-        int64_t coff[MAXN];
+        int coff[MAXN];
         if (!IDENT) {
 #pragma unroll
-            for (int k = 0; k < MAXN; ++k) coff[k] = col_off(ix0 + min(k, ncols - 1));
+            for (int k = 0; k < MAXN; ++k) coff[k] = col_idx(ix0 + min(k, ncols - 1));
         }
         // lengths of the cells' top sides inside the footprint: the previous row's bottom sides
         float lenTop[MAXN];
 #pragma unroll
         for (int k = 0; k < MAXN; ++k) lenTop[k] = aai_overlap1_f32(xlT, xrT, e0 + (float)k);
+        // Source values are fetched one row ahead of their use (the loads of row r+1 are in flight while the areas of
+        // row r are computed): the accumulate at the end of a row never waits for its own row's loads.
+        // (Single-channel kernels only: three channels would need 30 staging registers.)
+        constexpr bool PREFETCH = NC == 1;
+        float cur[MAXN][NC];
+        auto fetch = [&](int r, float (&v)[MAXN][NC]) {
+            if (IDENT)
+                rowp = rowp0 + (int64_t)r * kp.src_pitch;
+            else
+                rowp = (const char *)kp.src + row_off(jy0 + r);
+#pragma unroll
+            for (int k = 0; k < MAXN; ++k) {
+#pragma unroll
+                for (int ch = 0; ch < NC; ++ch) v[k][ch] = 0.0f;
+                if (k < ncols) {  // columns beyond the footprint box are never read (their area is exactly 0)
+                    const char *p = IDENT ? rowp + k * ESZ : rowp + (int64_t)coff[k] * cstride;
+#pragma unroll
+                    for (int ch = 0; ch < NC; ++ch) v[k][ch] = LoadF<TI>::get(p + ch * (int)sizeof(TI));
+                }
+            }
+        };
+        if (PREFETCH) fetch(0, cur);
 #pragma unroll kRowUnroll
         for (int r = 0; r < nrows; ++r) {
+            float nxt[MAXN][NC];
+            if (PREFETCH) {
+                if (r + 1 < nrows) fetch(r + 1, nxt);
+            } else {
+                rowp = IDENT ? rowp0 + (int64_t)r * kp.src_pitch : (const char *)kp.src + row_off(jy0 + r);
+            }
             const float ry = (float)(dj0 + r) - fy;
             float xlB, xrB;
             aai_chord_h_f32(g, ry + 0.5f, xlB, xrB);
             const float ey = ry - 0.5f;
             float lenL = aai_overlap1_f32(yt[0], yb[0], ey);
             const float ur = -ry * g.sn, vr = ry * g.cs;
-            const int j = jy0 + r;
-            if (IDENT)
-                rowp = rowp0 + (int64_t)r * kp.src_pitch;
-            else
-                rowp = (const char *)kp.src + row_off(j);
-            // load + accumulate one cell (predicated: columns beyond the footprint box are never read)
             auto take = [&](int k, float area) {
-                if (k < ncols) {
-                    const char *p = IDENT ? rowp + k * ESZ : rowp + coff[k];
+                if (PREFETCH) {
+#pragma unroll
+                    for (int ch = 0; ch < NC; ++ch) acc[ch] = fmaf(cur[k][ch], area, acc[ch]);
+                } else if (k < ncols) {  // load at the point of use
+                    const char *p = IDENT ? rowp + k * ESZ : rowp + (int64_t)coff[k] * cstride;
 #pragma unroll
                     for (int ch = 0; ch < NC; ++ch)
                         acc[ch] = fmaf(LoadF<TI>::get(p + ch * (int)sizeof(TI)), area, acc[ch]);
@@ -185,6 +219,12 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 const float area = aai_cell_exact_f32(g, u0, v0, lenT, lenB, lenL, lenR);
                 take(k, area);
             }
+            if (PREFETCH) {
+#pragma unroll
+                for (int k = 0; k < MAXN; ++k)
+#pragma unroll
+                    for (int ch = 0; ch < NC; ++ch) cur[k][ch] = nxt[k][ch];
+            }
         }
         // Total overlap: the exact areas of a footprint inside the image add up to L^2 (border pixels never get here).
         sumA = g.area_total;
@@ -218,8 +258,12 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         redo = worst < g.tau || sumA < 0.25f;
     }
     if (redo) {
-        double s64, a64[NC];
-        pixel_f64<TI, NC>(kp, cx, cy, ix0, ix1, jy0, jy1, s64, a64);
+        // rare path: geometry recomputed here so that it does not occupy registers across the FP32 loop
+        double s64, a64[NC], cx2, cy2;
+        int i0, i1, j0, j1;
+        pixel_centre(kp, x, y, cx2, cy2);
+        cell_range(kp, cx2, cy2, i0, i1, j0, j1);
+        pixel_f64<TI, NC>(kp, cx2, cy2, i0, i1, j0, j1, s64, a64);
         const bool ok = DBL_EPSILON < fabs(s64);
 #pragma unroll
         for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, ok ? a64[ch] / s64 : 0.0);
