@@ -123,20 +123,18 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         auto div_s = [&](int e) -> int64_t {
             return (int64_t)(kp.scale != 1 ? __umulhi((unsigned)e, kp.div_magic) : (unsigned)e);
         };
-        // column part as a 32-bit source index (row or column of the source) times a 64-bit stride
-        const int64_t cstride = swapped ? kp.src_pitch : (int64_t)ESZ;
-        auto col_idx = [&](int i) -> int {
-            return swapped ? (int)div_s(kp.e_ayi * i + kp.e_ay0) - kp.src_y0 : (int)div_s(kp.e_axi * i + kp.e_ax0);
+        auto col_off = [&](int i) -> int64_t {
+            return swapped ? (div_s(kp.e_ayi * i + kp.e_ay0) - kp.src_y0) * kp.src_pitch
+                           : div_s(kp.e_axi * i + kp.e_ax0) * ESZ;
         };
-        auto col_off = [&](int i) -> int64_t { return (int64_t)col_idx(i) * cstride; };
         auto row_off = [&](int j) -> int64_t {
             return swapped ? div_s(kp.e_axj * j + kp.e_ax0) * ESZ
                            : (div_s(kp.e_ayj * j + kp.e_ay0) - kp.src_y0) * kp.src_pitch;
         };
-        int coff[MAXN];
+        int64_t coff[MAXN];
         if (!IDENT) {
 #pragma unroll
-            for (int k = 0; k < MAXN; ++k) coff[k] = col_idx(ix0 + min(k, ncols - 1));
+            for (int k = 0; k < MAXN; ++k) coff[k] = col_off(ix0 + min(k, ncols - 1));
         }
         // lengths of the cells' top sides inside the footprint: the previous row's bottom sides
         float lenTop[MAXN];
@@ -157,7 +155,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
 #pragma unroll
                 for (int ch = 0; ch < NC; ++ch) v[k][ch] = 0.0f;
                 if (k < ncols) {  // columns beyond the footprint box are never read (their area is exactly 0)
-                    const char *p = IDENT ? rowp + k * ESZ : rowp + (int64_t)coff[k] * cstride;
+                    const char *p = IDENT ? rowp + k * ESZ : rowp + coff[k];
 #pragma unroll
                     for (int ch = 0; ch < NC; ++ch) v[k][ch] = LoadF<TI>::get(p + ch * (int)sizeof(TI));
                 }
@@ -183,7 +181,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
 #pragma unroll
                     for (int ch = 0; ch < NC; ++ch) acc[ch] = fmaf(cur[k][ch], area, acc[ch]);
                 } else if (k < ncols) {  // load at the point of use
-                    const char *p = IDENT ? rowp + k * ESZ : rowp + (int64_t)coff[k] * cstride;
+                    const char *p = IDENT ? rowp + k * ESZ : rowp + coff[k];
 #pragma unroll
                     for (int ch = 0; ch < NC; ++ch)
                         acc[ch] = fmaf(LoadF<TI>::get(p + ch * (int)sizeof(TI)), area, acc[ch]);

@@ -6,9 +6,12 @@
 // HBM-bound by contract (each source byte read once, each canvas byte written once).  One CTA = one canvas tile
 // TW x TH.  Its source window is staged into shared memory by ONE 2-D TMA tile load (cp.async.bulk.tensor.2d through
 // a CUtensorMap, completion on an mbarrier; out-of-image parts of the box are zero-filled by the hardware and carry
-// weight 0).  Two banded 1-D passes run out of shared memory: rows (horizontal taps, weights in registers) into an
-// intermediate tile, then columns (vertical taps, weights broadcast from shared memory) to the coalesced store.
-// Several CTAs are resident per SM, so one CTA's TMA load overlaps the other CTAs' passes.
+// weight 0).  The two banded 1-D passes run out of that tile with the intermediate in registers: for every canvas pixel
+// the horizontal taps of each of its source rows (weights in registers, taps read as aligned vectors so that the
+// stride-L accesses of a warp do not collide on shared-memory banks), then the vertical taps (weights broadcast from
+// shared memory), then the coalesced store.  (A first version wrote the horizontal pass to a shared-memory tile and
+// synchronised: 3x the instructions, issue-bound at 64 %; see profiles/.)  Several CTAs are resident per SM, so one
+// CTA's TMA load overlaps the other CTAs' arithmetic.
 //
 // A batch of equally strided images is ONE launch: the tensor map is rank 3 (x, y, image), blockIdx.y = image.
 //
@@ -91,16 +94,33 @@ __device__ __forceinline__ void axis_taps(double c, double h, int limit, int &fi
     }
 }
 
+// aligned vector of source elements in shared memory: 8 bytes for 4-byte elements, otherwise one element
+template <typename TI>
+struct TapVec {
+    static constexpr int N = 1;
+    static __device__ __forceinline__ void load(const TI *p, TI (&v)[1]) { v[0] = *p; }
+};
+template <>
+struct TapVec<float> {
+    static constexpr int N = 2;
+    static __device__ __forceinline__ void load(const float *p, float (&v)[2]) {
+        const float2 t = *reinterpret_cast<const float2 *>(p);
+        v[0] = t.x;
+        v[1] = t.y;
+    }
+};
+
 template <typename TI, typename TO, typename TA, int TW, int MAXT>
 __global__ void __launch_bounds__(SEP_THREADS)
     separable_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ AaiKernelParams kp,
                          const SepParams sp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int RG = SEP_THREADS / TW;  // row groups
+    constexpr int VEC = TapVec<TI>::N;
+    constexpr int NV = (MAXT + 2 * (VEC - 1)) / VEC;  // aligned vectors that cover MAXT taps from any start offset
     TI *tile = reinterpret_cast<TI *>(smem_raw);
     const size_t tile_bytes = ((size_t)sp.bw * sp.bh * sizeof(TI) + 127) / 128 * 128;
-    TA *hbuf = reinterpret_cast<TA *>(smem_raw + tile_bytes);                       // [bh][TW]
-    TA *wyw = hbuf + (size_t)sp.bh * TW;                                             // [th][MAXT]
+    TA *wyw = reinterpret_cast<TA *>(smem_raw + tile_bytes);                         // [th][MAXT]
     TA *wys = wyw + (size_t)sp.th * MAXT;                                            // [th] 1/sum
     int *wyf = reinterpret_cast<int *>(wys + sp.th);                                 // [th] first row (tile-relative)
     uint64_t *bar = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(wyf + sp.th) + 7) / 8 * 8);
@@ -161,30 +181,44 @@ __global__ void __launch_bounds__(SEP_THREADS)
         wys[tid] = s;
         wyf[tid] = first - oy;
     }
-    // clamp the tap window into the box (taps beyond it have weight 0 by construction of the box size)
-    cfirst = max(0, min(cfirst, sp.bw - MAXT));
+    // clamp the tap window into the box (taps beyond it have weight 0 by construction of the box size), then widen it
+    // to whole aligned vectors: weights wv[] = wx[] shifted by the start offset inside the first vector, zero elsewhere
+    cfirst = max(0, min(cfirst, sp.bw - MAXT - 2 * (VEC - 1)));
+    const int cbase = cfirst / VEC * VEC, shift = cfirst - cbase;
+    TA wv[NV * VEC];
+#pragma unroll
+    for (int q = 0; q < NV * VEC; ++q) {
+        TA v = (TA)0;
+#pragma unroll
+        for (int t = 0; t < MAXT; ++t) v = (q - shift == t) ? wx[t] : v;
+        wv[q] = v;
+    }
+    __syncthreads();  // row weights visible
 
     mbar_wait(bar, 0);
 
-    // pass 1: horizontal taps, every source row of the window
-    for (int r = rg; r < sp.bh; r += RG) {
-        const TI *row = tile + (size_t)r * sp.bw + cfirst;
-        TA acc = (TA)0;
-#pragma unroll
-        for (int t = 0; t < MAXT; ++t) acc += wx[t] * (TA)row[t];
-        hbuf[(size_t)r * TW + xo] = acc;
-    }
-    __syncthreads();
-
-    // pass 2: vertical taps, coalesced store
     if (x < kp.dst_w) {
         for (int yo = rg; yo < sp.th; yo += RG) {
             const int y = y0 + yo;
             if (y >= kp.row1) break;
             const int rf = max(0, min(wyf[yo], sp.bh - MAXT));
+            const TI *row = tile + (size_t)rf * sp.bw + cbase;
             TA acc = (TA)0;
 #pragma unroll
-            for (int t = 0; t < MAXT; ++t) acc += wyw[yo * MAXT + t] * hbuf[(size_t)(rf + t) * TW + xo];
+            for (int t = 0; t < MAXT; ++t) {
+                // horizontal taps of source row rf + t ...
+                TA hs = (TA)0;
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    TI v[VEC];
+                    TapVec<TI>::load(row + q * VEC, v);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) hs += wv[q * VEC + e] * (TA)v[e];
+                }
+                // ... then its vertical tap
+                acc += wyw[yo * MAXT + t] * hs;
+                row += sp.bw;
+            }
             const TA total = sumx * wys[yo];
             const double out = ((double)total > DBL_EPSILON) ? (double)(acc / total) : 0.0;  // Source.cpp:577
             char *drow = (char *)kp.dst + (int64_t)blockIdx.y * kp.dst_batch_stride + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
@@ -234,14 +268,15 @@ cudaError_t launch_sep(const AaiKernelParams &kp, cudaStream_t stream) {
     sp.th = 32;
     // the window must hold MAXT taps starting at the first cell of the LAST column / row of the tile
     // (+ align-1 columns because the window origin is rounded down to a 16-byte boundary)
-    sp.bw = ((int)ceil((TW - 1) * L) + MAXT + 3 + (align - 1) + align - 1) / align * align;
+    // (+ 2(VEC-1) so that the taps can be read as whole aligned vectors)
+    sp.bw = ((int)ceil((TW - 1) * L) + MAXT + 3 + 2 * (TapVec<TI>::N - 1) + (align - 1) + align - 1) / align * align;
     sp.bh = (int)ceil((sp.th - 1) * L) + MAXT + 3;
     if (sp.bw > 256 || sp.bh > 256 || sp.bw < MAXT || sp.bh < MAXT) return cudaErrorNotSupported;
     sp.tiles_x = (kp.dst_w + TW - 1) / TW;
     const int rows = kp.row1 - kp.row0;
     const int tiles_y = (rows + sp.th - 1) / sp.th;
     size_t smem = ((size_t)sp.bw * sp.bh * esz + 127) / 128 * 128;
-    smem += ((size_t)sp.bh * TW + (size_t)sp.th * MAXT + sp.th) * sizeof(TA) + (size_t)sp.th * sizeof(int) + 16;
+    smem += ((size_t)sp.th * MAXT + sp.th) * sizeof(TA) + (size_t)sp.th * sizeof(int) + 16;
     if (smem > 200 * 1024) return cudaErrorNotSupported;
 
     CUtensorMap tmap;
