@@ -29,12 +29,15 @@ using namespace aai_dev;
 
 namespace {
 
-constexpr int SEP_THREADS = 256;
+constexpr int SEP_THREADS = 256;   // consumer threads (canvas pixels); one more warp produces (TMA + row weights)
+constexpr int SEP_BLOCK = SEP_THREADS + 32;
 
 struct SepParams {
     int tw, th;  // canvas tile
     int bw, bh;  // TMA box = source window of one tile (elements, rows)
-    int tiles_x;
+    int tiles_x, tiles_y;
+    int tiles_per_cta;  // consecutive tile rows one CTA walks through
+    int stages;         // source windows in the shared-memory ring (stages - 1 loads in flight while one is evaluated)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -110,76 +113,110 @@ struct TapVec<float> {
     }
 };
 
+template <typename TA>
+__device__ __forceinline__ TA sep_normalise(TA acc, TA total) {  // Source.cpp:577
+    return ((double)total > DBL_EPSILON) ? acc / total : (TA)0;
+}
+template <>
+__device__ __forceinline__ float sep_normalise<float>(float acc, float total) {
+    const float q = __fdividef(acc, total);  // branch-free (<= 2 ulp); the select discards inf/NaN of an empty footprint
+    return total > (float)DBL_EPSILON ? q : 0.0f;
+}
+
+// One CTA walks DOWN a strip of canvas tiles (same canvas columns, consecutive tile rows): the column weights and
+// their vector layout are computed once per CTA; the source windows go through a ring of shared-memory buffers that a
+// dedicated producer warp keeps full (TMA load of tile t+S-1 and its row weights while the eight consumer warps
+// evaluate tile t), so HBM never waits for the arithmetic and no consumer warp carries the FP64 weight set-up.
 template <typename TI, typename TO, typename TA, int TW, int MAXT>
-__global__ void __launch_bounds__(SEP_THREADS)
+__global__ void __launch_bounds__(SEP_BLOCK)
     separable_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ AaiKernelParams kp,
                          const SepParams sp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int RG = SEP_THREADS / TW;  // row groups
     constexpr int VEC = TapVec<TI>::N;
     constexpr int NV = (MAXT + 2 * (VEC - 1)) / VEC;  // aligned vectors that cover MAXT taps from any start offset
-    TI *tile = reinterpret_cast<TI *>(smem_raw);
     const size_t tile_bytes = ((size_t)sp.bw * sp.bh * sizeof(TI) + 127) / 128 * 128;
-    TA *wyw = reinterpret_cast<TA *>(smem_raw + tile_bytes);                         // [th][MAXT]
-    TA *wys = wyw + (size_t)sp.th * MAXT;                                            // [th] 1/sum
-    int *wyf = reinterpret_cast<int *>(wys + sp.th);                                 // [th] first row (tile-relative)
-    uint64_t *bar = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(wyf + sp.th) + 7) / 8 * 8);
+    const size_t wgt_bytes = (((size_t)sp.th * MAXT + sp.th) * sizeof(TA) + (size_t)sp.th * sizeof(int) + 15) / 16 * 16;
+    // layout: tile[stages], weights[stages], barriers[stages]
+    const int S = sp.stages;
+    unsigned char *wgt_raw = smem_raw + (size_t)S * tile_bytes;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wgt_raw + (size_t)S * wgt_bytes);
 
     const int tid = threadIdx.x;
-    const int tx = blockIdx.x % sp.tiles_x, ty = blockIdx.x / sp.tiles_x;
-    const int x0 = tx * TW, y0 = kp.row0 + ty * sp.th;
+    const int tx = blockIdx.x % sp.tiles_x, seg = blockIdx.x / sp.tiles_x;
+    const int ty0 = seg * sp.tiles_per_cta, ntile = min(sp.tiles_per_cta, sp.tiles_y - ty0);
+    const int x0 = tx * TW;
     const double h = kp.shape.half;
 
-    // source window origin of this tile (expanded frame == source frame on this path)
-    double c0x, c0y;
-    pixel_centre(kp, x0, y0, c0x, c0y);
+    // source window origin of tile row t of this strip (expanded frame == source frame on this path).
     // TMA needs the box to start on a 16-byte boundary of the innermost dimension (measured on B200: a misaligned
-    // start coordinate raises cudaErrorIllegalInstruction), so the window origin is rounded down to ALIGN elements
+    // start coordinate raises cudaErrorIllegalInstruction), so the window's x origin is rounded down to ALIGN elements
     constexpr int ALIGN = 16 / (int)sizeof(TI);
+    double c0x, c0y;
+    pixel_centre(kp, x0, kp.row0 + ty0 * sp.th, c0x, c0y);
     const int ox_raw = __double2int_rd(c0x - h - 0.5);
     const int ox = (ox_raw >= 0 ? ox_raw / ALIGN : -((-ox_raw + ALIGN - 1) / ALIGN)) * ALIGN;
-    const int oy = __double2int_rd(c0y - h - 0.5);
+    auto origin_y = [&](int t) {
+        double ax, ay;
+        pixel_centre(kp, x0, kp.row0 + (ty0 + t) * sp.th, ax, ay);
+        return __double2int_rd(ay - h - 0.5);
+    };
+    auto issue = [&](int t) {  // one thread: TMA load of tile t's window into buffer t % S
+        uint64_t *bb = bar + (t % S);
+        mbar_expect_tx(bb, (uint32_t)(sp.bw * sp.bh * sizeof(TI)));
+        tma_load_3d(smem_raw + (size_t)(t % S) * tile_bytes, &tmap, bb, ox, origin_y(t) - kp.src_y0, (int)blockIdx.y);
+    };
+    auto row_weights = [&](int t, int lane) {  // producer warp: vertical taps of tile t's canvas rows into weights[t % S]
+        TA *wyw = reinterpret_cast<TA *>(wgt_raw + (size_t)(t % S) * wgt_bytes);  // [th][MAXT]
+        TA *wys = wyw + (size_t)sp.th * MAXT;                                      // [th] sum
+        int *wyf = reinterpret_cast<int *>(wys + sp.th);                            // [th] first row (tile-relative)
+        const int oy = origin_y(t);
+        for (int r = lane; r < sp.th; r += 32) {
+            const int y = kp.row0 + (ty0 + t) * sp.th + r;
+            TA w[MAXT], sy = (TA)0;
+            int first = oy;
+            if (y < kp.row1) {
+                double cx, cy;
+                pixel_centre(kp, x0, y, cx, cy);
+                axis_taps<TA, MAXT>(cy, h, kp.mod_h, first, w, sy);
+            } else {
+#pragma unroll
+                for (int k = 0; k < MAXT; ++k) w[k] = (TA)0;
+            }
+#pragma unroll
+            for (int k = 0; k < MAXT; ++k) wyw[r * MAXT + k] = w[k];
+            wys[r] = sy;
+            wyf[r] = first - oy;
+        }
+    };
+    const bool producer = tid >= SEP_THREADS;
+    const int lane = tid & 31;
 
     if (tid == 0) {
-        mbar_init(bar, 1);
+        for (int k = 0; k < S; ++k) mbar_init(bar + k, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) {
-        mbar_expect_tx(bar, (uint32_t)(sp.bw * sp.bh * sizeof(TI)));
-        tma_load_3d(tile, &tmap, bar, ox, oy - kp.src_y0, (int)blockIdx.y);
+    if (producer) {
+        for (int t = 0; t < S - 1 && t < ntile; ++t) {
+            if (lane == 0) issue(t);
+            row_weights(t, lane);
+        }
     }
 
-    // while the TMA load is in flight: per-column weights (registers) and per-row weights (shared memory)
+    // per-column weights (registers), once per strip, while the first load is in flight
     const int xo = tid % TW, rg = tid / TW;
     const int x = x0 + xo;
     int cfirst = 0;
     TA wx[MAXT], sumx = (TA)0;
-    if (x < kp.dst_w) {
+    if (!producer && x < kp.dst_w) {
         double cx, cy;
-        pixel_centre(kp, x, y0, cx, cy);
+        pixel_centre(kp, x, kp.row0, cx, cy);
         axis_taps<TA, MAXT>(cx, h, kp.mod_w, cfirst, wx, sumx);
         cfirst -= ox;
     } else {
 #pragma unroll
         for (int t = 0; t < MAXT; ++t) wx[t] = (TA)0;
-    }
-    if (tid < sp.th) {
-        const int y = y0 + tid;
-        TA w[MAXT], s = (TA)0;
-        int first = oy;
-        if (y < kp.row1) {
-            double cx, cy;
-            pixel_centre(kp, x0, y, cx, cy);
-            axis_taps<TA, MAXT>(cy, h, kp.mod_h, first, w, s);
-        } else {
-#pragma unroll
-            for (int t = 0; t < MAXT; ++t) w[t] = (TA)0;
-        }
-#pragma unroll
-        for (int t = 0; t < MAXT; ++t) wyw[tid * MAXT + t] = w[t];
-        wys[tid] = s;
-        wyf[tid] = first - oy;
     }
     // clamp the tap window into the box (taps beyond it have weight 0 by construction of the box size), then widen it
     // to whole aligned vectors: weights wv[] = wx[] shifted by the start offset inside the first vector, zero elsewhere
@@ -193,37 +230,72 @@ __global__ void __launch_bounds__(SEP_THREADS)
         for (int t = 0; t < MAXT; ++t) v = (q - shift == t) ? wx[t] : v;
         wv[q] = v;
     }
-    __syncthreads();  // row weights visible
+    __syncthreads();  // row weights of the first tiles visible
 
-    mbar_wait(bar, 0);
-
-    if (x < kp.dst_w) {
-        for (int yo = rg; yo < sp.th; yo += RG) {
-            const int y = y0 + yo;
-            if (y >= kp.row1) break;
-            const int rf = max(0, min(wyf[yo], sp.bh - MAXT));
-            const TI *row = tile + (size_t)rf * sp.bw + cbase;
-            TA acc = (TA)0;
-#pragma unroll
-            for (int t = 0; t < MAXT; ++t) {
-                // horizontal taps of source row rf + t ...
-                TA hs = (TA)0;
-#pragma unroll
-                for (int q = 0; q < NV; ++q) {
-                    TI v[VEC];
-                    TapVec<TI>::load(row + q * VEC, v);
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) hs += wv[q * VEC + e] * (TA)v[e];
-                }
-                // ... then its vertical tap
-                acc += wyw[yo * MAXT + t] * hs;
-                row += sp.bw;
+    for (int t = 0; t < ntile; ++t) {
+        if (producer) {
+            // tile t+S-1: load + row weights (its buffers were last read in iteration t-1, which ended with a barrier)
+            if (t + S - 1 < ntile) {
+                if (lane == 0) issue(t + S - 1);
+                row_weights(t + S - 1, lane);
             }
-            const TA total = sumx * wys[yo];
-            const double out = ((double)total > DBL_EPSILON) ? (double)(acc / total) : 0.0;  // Source.cpp:577
-            char *drow = (char *)kp.dst + (int64_t)blockIdx.y * kp.dst_batch_stride + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
-            store_dst<TO>(drow, x, out);
+            __syncthreads();
+            continue;
         }
+        const int b = t % S;
+        const TI *tile = reinterpret_cast<const TI *>(smem_raw + (size_t)b * tile_bytes);
+        const TA *wyw = reinterpret_cast<const TA *>(wgt_raw + (size_t)b * wgt_bytes);
+        const TA *wys = wyw + (size_t)sp.th * MAXT;
+        const int *wyf = reinterpret_cast<const int *>(wys + sp.th);
+        const int y0 = kp.row0 + (ty0 + t) * sp.th;
+        mbar_wait(bar + b, (uint32_t)((t / S) & 1));
+        if (x < kp.dst_w) {
+            // U independent canvas rows at a time, stage by stage, so that the shared-memory loads of U pixels are in
+            // flight together (one dependent chain per pixel is latency-bound: few resident warps per SM)
+            constexpr int U = 4;
+            for (int yb = rg; yb < sp.th; yb += RG * U) {
+                const TI *row[U];
+                int yo[U];
+                TA acc[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    yo[u] = min(yb + u * RG, sp.th - 1);
+                    const int rf = max(0, min(wyf[yo[u]], sp.bh - MAXT));
+                    row[u] = tile + (size_t)rf * sp.bw + cbase;
+                    acc[u] = (TA)0;
+                }
+#pragma unroll
+                for (int k = 0; k < MAXT; ++k) {
+                    TI v[U][NV][VEC];
+                    TA wk[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {  // all loads of this source row first ...
+#pragma unroll
+                        for (int q = 0; q < NV; ++q) TapVec<TI>::load(row[u] + q * VEC, v[u][q]);
+                        wk[u] = wyw[yo[u] * MAXT + k];
+                        row[u] += sp.bw;
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {  // ... then its horizontal taps and its vertical tap
+                        TA hs = (TA)0;
+#pragma unroll
+                        for (int q = 0; q < NV; ++q)
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) hs += wv[q * VEC + e] * (TA)v[u][q][e];
+                        acc[u] += wk[u] * hs;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int y = y0 + yb + u * RG;
+                    const TA out = sep_normalise<TA>(acc[u], sumx * wys[yo[u]]);
+                    char *drow = (char *)kp.dst + (int64_t)blockIdx.y * kp.dst_batch_stride +
+                                 (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
+                    if (yb + u * RG < sp.th && y < kp.row1) store_dst<TO>(drow, x, (double)out);
+                }
+            }
+        }
+        __syncthreads();  // tile t's buffers are free, the row weights just written are visible
     }
 }
 
@@ -265,22 +337,52 @@ cudaError_t launch_sep(const AaiKernelParams &kp, cudaStream_t stream) {
     const int esz = (int)sizeof(TI), align = 16 / esz;
     SepParams sp;
     sp.tw = TW;
-    sp.th = 32;
-    // the window must hold MAXT taps starting at the first cell of the LAST column / row of the tile
-    // (+ align-1 columns because the window origin is rounded down to a 16-byte boundary)
-    // (+ 2(VEC-1) so that the taps can be read as whole aligned vectors)
-    sp.bw = ((int)ceil((TW - 1) * L) + MAXT + 3 + 2 * (TapVec<TI>::N - 1) + (align - 1) + align - 1) / align * align;
-    sp.bh = (int)ceil((sp.th - 1) * L) + MAXT + 3;
-    if (sp.bw > 256 || sp.bh > 256 || sp.bw < MAXT || sp.bh < MAXT) return cudaErrorNotSupported;
-    sp.tiles_x = (kp.dst_w + TW - 1) / TW;
+    sp.stages = 2;
+    if (const char *e = getenv("AAI_SEP_STAGES")) sp.stages = atoi(e);  // developer knobs (sweeps in profiles/)
+    if (sp.stages < 2 || sp.stages > 8) return cudaErrorNotSupported;
+    const int batch = kp.batch > 0 ? kp.batch : 1;
     const int rows = kp.row1 - kp.row0;
-    const int tiles_y = (rows + sp.th - 1) / sp.th;
-    size_t smem = ((size_t)sp.bw * sp.bh * esz + 127) / 128 * 128;
-    smem += ((size_t)sp.th * MAXT + sp.th) * sizeof(TA) + (size_t)sp.th * sizeof(int) + 16;
-    if (smem > 200 * 1024) return cudaErrorNotSupported;
+    // tile height: the tallest of 48 / 32 / 16 canvas rows whose ring of source windows leaves room for two CTAs per SM
+    // (measured on config 5: 48 rows x 2 stages, 2 CTAs/SM is the fastest -- fewer halo rows, 54 KB per TMA load)
+    size_t tile_bytes = 0, wgt_bytes = 0, smem = 0;
+    bool found = false;
+    for (int th : {48, 32, 16}) {
+        if (const char *e = getenv("AAI_SEP_TH")) th = atoi(e);
+        if (th < 8 || th > 256 || th % (SEP_THREADS / TW) != 0) return cudaErrorNotSupported;
+        sp.th = th;
+        // the window must hold MAXT taps starting at the first cell of the LAST column / row of the tile
+        // (+ align-1 columns because the window origin is rounded down to a 16-byte boundary)
+        // (+ 2(VEC-1) so that the taps can be read as whole aligned vectors)
+        sp.bw = ((int)ceil((TW - 1) * L) + MAXT + 3 + 2 * (TapVec<TI>::N - 1) + (align - 1) + align - 1) / align * align;
+        sp.bh = (int)ceil((sp.th - 1) * L) + MAXT + 3;
+        tile_bytes = ((size_t)sp.bw * sp.bh * esz + 127) / 128 * 128;
+        wgt_bytes = (((size_t)sp.th * MAXT + sp.th) * sizeof(TA) + (size_t)sp.th * sizeof(int) + 15) / 16 * 16;
+        smem = sp.stages * (tile_bytes + wgt_bytes) + 8 * sp.stages + 16;
+        if (sp.bw <= 256 && sp.bh <= 256 && sp.bw >= MAXT && sp.bh >= MAXT && smem <= 112 * 1024) {
+            found = true;
+            break;
+        }
+        if (getenv("AAI_SEP_TH")) break;
+    }
+    if (!found && (sp.bw > 256 || sp.bh > 256 || sp.bw < MAXT || sp.bh < MAXT || smem > 220 * 1024))
+        return cudaErrorNotSupported;
+    sp.tiles_x = (kp.dst_w + TW - 1) / TW;
+    sp.tiles_y = (rows + sp.th - 1) / sp.th;
+    // strips are cut into segments so that the grid still fills the device (~4 CTAs per SM) when the batch is small
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (sm_count <= 0) sm_count = 148;
+    }
+    const int want_ctas = 4 * sm_count;
+    int segs = (want_ctas + sp.tiles_x * batch - 1) / (sp.tiles_x * batch);
+    segs = segs < 1 ? 1 : (segs > sp.tiles_y ? sp.tiles_y : segs);
+    sp.tiles_per_cta = (sp.tiles_y + segs - 1) / segs;
+    segs = (sp.tiles_y + sp.tiles_per_cta - 1) / sp.tiles_per_cta;
 
     CUtensorMap tmap;
-    const int batch = kp.batch > 0 ? kp.batch : 1;
     const cuuint64_t gdim[3] = {(cuuint64_t)kp.src_w, (cuuint64_t)kp.src_rows, (cuuint64_t)batch};
     const cuuint64_t gstride[2] = {(cuuint64_t)kp.src_pitch,
                                    (cuuint64_t)(batch > 1 ? kp.src_batch_stride : kp.src_pitch * (int64_t)kp.src_rows)};
@@ -293,12 +395,12 @@ cudaError_t launch_sep(const AaiKernelParams &kp, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) return cudaErrorNotSupported;
     if (getenv("AAI_DEBUG"))
         fprintf(stderr, "[aai] separable TMA: TI=%d bytes TA=%d bytes TW=%d MAXT=%d box %dx%d tiles %dx%d smem %zu src %p pitch %lld "
-                "w %d rows %d\n", esz, (int)sizeof(TA), TW, MAXT, sp.bw, sp.bh, sp.tiles_x, tiles_y, smem, kp.src,
+                "w %d rows %d\n", esz, (int)sizeof(TA), TW, MAXT, sp.bw, sp.bh, sp.tiles_x, sp.tiles_y, smem, kp.src,
                 (long long)kp.src_pitch, kp.src_w, kp.src_rows);
     auto kernel = separable_tma_kernel<TI, TO, TA, TW, MAXT>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kernel<<<dim3(sp.tiles_x * tiles_y, batch), SEP_THREADS, smem, stream>>>(tmap, kp, sp);
+    kernel<<<dim3(sp.tiles_x * segs, batch), SEP_BLOCK, smem, stream>>>(tmap, kp, sp);
     return cudaGetLastError();
 }
 

@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", type=int, default=4)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--arith", default="f64")
+ap.add_argument("--batch", type=int, default=0, help="config 5: slices per launch (aai_run_device_batch)")
 args = ap.parse_args()
 cfg = CONFIGS[args.config]
 dev = torch.device("cuda:0")
@@ -28,12 +29,24 @@ dst = torch.empty((plan.dst_h, plan.dst_w) + tail, dtype=torch.float32, device=d
 si, di = aai.tensor_image(src), aai.tensor_image(dst)
 arith = aai.ARITH_F32 if args.arith == "f32" else aai.ARITH_F64
 st = torch.cuda.current_stream().cuda_stream
+if args.batch:
+    srcs = torch.rand((args.batch, cfg["h"], cfg["w"]), dtype=torch.float32, device=dev) * 4096
+    dsts = torch.empty((args.batch, plan.dst_h, plan.dst_w), dtype=torch.float32, device=dev)
+    sis = [aai.tensor_image(srcs[i]) for i in range(args.batch)]
+    dis = [aai.tensor_image(dsts[i]) for i in range(args.batch)]
+
+    def run_device(plan, si, di, arith, stream):
+        aai.run_device_batch(plan, sis, dis, arith=arith, stream=stream)
+
+    aai_run = run_device
+else:
+    aai_run = aai.run_device
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-aai.run_device(plan, si, di, arith=arith, stream=st)
+aai_run(plan, si, di, arith=arith, stream=st)
 torch.cuda.synchronize()
 e0.record()
 for _ in range(args.steps):
-    aai.run_device(plan, si, di, arith=arith, stream=st)
+    aai_run(plan, si, di, arith=arith, stream=st)
 e1.record()
 torch.cuda.synchronize()
 print(f"{cfg['label']}: canvas {plan.dst_w}x{plan.dst_h}, {e0.elapsed_time(e1) / args.steps:.3f} ms per launch")
