@@ -113,6 +113,11 @@ struct TapVec<float> {
     }
 };
 
+template <typename TA, int MAXT>
+__host__ __device__ constexpr size_t sep_weight_bytes(int th) {
+    return ((size_t)th * ((MAXT + 1 + 3) / 4 * 4) * sizeof(TA) + (size_t)th * sizeof(int) + 15) / 16 * 16;
+}
+
 template <typename TA>
 __device__ __forceinline__ TA sep_normalise(TA acc, TA total) {  // Source.cpp:577
     return ((double)total > DBL_EPSILON) ? acc / total : (TA)0;
@@ -121,6 +126,25 @@ template <>
 __device__ __forceinline__ float sep_normalise<float>(float acc, float total) {
     const float q = __fdividef(acc, total);  // branch-free (<= 2 ulp); the select discards inf/NaN of an empty footprint
     return total > (float)DBL_EPSILON ? q : 0.0f;
+}
+
+// per-canvas-row record in shared memory: MAXT vertical weights followed by their sum, padded to a multiple of four
+// elements so that a float record is read with 16-byte loads
+template <typename TA, int N>
+__device__ __forceinline__ void load_record(const TA *rec, TA (&w)[N]) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) w[k] = rec[k];
+}
+template <int N>
+__device__ __forceinline__ void load_record(const float *rec, float (&w)[N]) {
+#pragma unroll
+    for (int k = 0; k < N; k += 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(rec + k);
+        w[k] = t.x;
+        if (k + 1 < N) w[k + 1] = t.y;
+        if (k + 2 < N) w[k + 2] = t.z;
+        if (k + 3 < N) w[k + 3] = t.w;
+    }
 }
 
 // One CTA walks DOWN a strip of canvas tiles (same canvas columns, consecutive tile rows): the column weights and
@@ -135,9 +159,10 @@ __global__ void __launch_bounds__(SEP_BLOCK)
     constexpr int RG = SEP_THREADS / TW;  // row groups
     constexpr int VEC = TapVec<TI>::N;
     constexpr int NV = (MAXT + 2 * (VEC - 1)) / VEC;  // aligned vectors that cover MAXT taps from any start offset
+    constexpr int RS = (MAXT + 1 + 3) / 4 * 4;  // record stride (elements)
     const size_t tile_bytes = ((size_t)sp.bw * sp.bh * sizeof(TI) + 127) / 128 * 128;
-    const size_t wgt_bytes = (((size_t)sp.th * MAXT + sp.th) * sizeof(TA) + (size_t)sp.th * sizeof(int) + 15) / 16 * 16;
-    // layout: tile[stages], weights[stages], barriers[stages]
+    const size_t wgt_bytes = sep_weight_bytes<TA, MAXT>(sp.th);
+    // layout: tile[stages], weights[stages] (records [th][RS], then element offsets [th]), barriers[stages]
     const int S = sp.stages;
     unsigned char *wgt_raw = smem_raw + (size_t)S * tile_bytes;
     uint64_t *bar = reinterpret_cast<uint64_t *>(wgt_raw + (size_t)S * wgt_bytes);
@@ -167,9 +192,8 @@ __global__ void __launch_bounds__(SEP_BLOCK)
         tma_load_3d(smem_raw + (size_t)(t % S) * tile_bytes, &tmap, bb, ox, origin_y(t) - kp.src_y0, (int)blockIdx.y);
     };
     auto row_weights = [&](int t, int lane) {  // producer warp: vertical taps of tile t's canvas rows into weights[t % S]
-        TA *wyw = reinterpret_cast<TA *>(wgt_raw + (size_t)(t % S) * wgt_bytes);  // [th][MAXT]
-        TA *wys = wyw + (size_t)sp.th * MAXT;                                      // [th] sum
-        int *wyf = reinterpret_cast<int *>(wys + sp.th);                            // [th] first row (tile-relative)
+        TA *rec = reinterpret_cast<TA *>(wgt_raw + (size_t)(t % S) * wgt_bytes);  // [th][RS]: weights, sum
+        int *off = reinterpret_cast<int *>(rec + (size_t)sp.th * RS);               // [th] element offset of the first row
         const int oy = origin_y(t);
         for (int r = lane; r < sp.th; r += 32) {
             const int y = kp.row0 + (ty0 + t) * sp.th + r;
@@ -184,9 +208,10 @@ __global__ void __launch_bounds__(SEP_BLOCK)
                 for (int k = 0; k < MAXT; ++k) w[k] = (TA)0;
             }
 #pragma unroll
-            for (int k = 0; k < MAXT; ++k) wyw[r * MAXT + k] = w[k];
-            wys[r] = sy;
-            wyf[r] = first - oy;
+            for (int k = 0; k < MAXT; ++k) rec[r * RS + k] = w[k];
+            rec[r * RS + MAXT] = sy;
+            // clamp the tap rows into the box (rows beyond it have weight 0 by construction of the box size)
+            off[r] = max(0, min(first - oy, sp.bh - MAXT)) * sp.bw;
         }
     };
     const bool producer = tid >= SEP_THREADS;
@@ -243,38 +268,35 @@ __global__ void __launch_bounds__(SEP_BLOCK)
             continue;
         }
         const int b = t % S;
-        const TI *tile = reinterpret_cast<const TI *>(smem_raw + (size_t)b * tile_bytes);
-        const TA *wyw = reinterpret_cast<const TA *>(wgt_raw + (size_t)b * wgt_bytes);
-        const TA *wys = wyw + (size_t)sp.th * MAXT;
-        const int *wyf = reinterpret_cast<const int *>(wys + sp.th);
+        const TI *tile = reinterpret_cast<const TI *>(smem_raw + (size_t)b * tile_bytes) + cbase;
+        const TA *rec = reinterpret_cast<const TA *>(wgt_raw + (size_t)b * wgt_bytes);
+        const int *off = reinterpret_cast<const int *>(rec + (size_t)sp.th * RS);
         const int y0 = kp.row0 + (ty0 + t) * sp.th;
+        const int ylim = min(sp.th, kp.row1 - y0);  // canvas rows of this tile that exist
         mbar_wait(bar + b, (uint32_t)((t / S) & 1));
         if (x < kp.dst_w) {
             // U independent canvas rows at a time, stage by stage, so that the shared-memory loads of U pixels are in
             // flight together (one dependent chain per pixel is latency-bound: few resident warps per SM)
             constexpr int U = 4;
+            char *out_row = (char *)kp.dst + (int64_t)blockIdx.y * kp.dst_batch_stride +
+                            (int64_t)(y0 + rg - kp.dst_y0) * kp.dst_pitch;
             for (int yb = rg; yb < sp.th; yb += RG * U) {
                 const TI *row[U];
-                int yo[U];
-                TA acc[U];
+                TA w[U][MAXT + 1], acc[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    yo[u] = min(yb + u * RG, sp.th - 1);
-                    const int rf = max(0, min(wyf[yo[u]], sp.bh - MAXT));
-                    row[u] = tile + (size_t)rf * sp.bw + cbase;
+                    const int yo = min(yb + u * RG, sp.th - 1);
+                    row[u] = tile + off[yo];
+                    load_record(rec + yo * RS, w[u]);
                     acc[u] = (TA)0;
                 }
 #pragma unroll
                 for (int k = 0; k < MAXT; ++k) {
                     TI v[U][NV][VEC];
-                    TA wk[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {  // all loads of this source row first ...
+                    for (int u = 0; u < U; ++u)  // all loads of this source row first ...
 #pragma unroll
-                        for (int q = 0; q < NV; ++q) TapVec<TI>::load(row[u] + q * VEC, v[u][q]);
-                        wk[u] = wyw[yo[u] * MAXT + k];
-                        row[u] += sp.bw;
-                    }
+                        for (int q = 0; q < NV; ++q) TapVec<TI>::load(row[u] + k * sp.bw + q * VEC, v[u][q]);
 #pragma unroll
                     for (int u = 0; u < U; ++u) {  // ... then its horizontal taps and its vertical tap
                         TA hs = (TA)0;
@@ -282,16 +304,14 @@ __global__ void __launch_bounds__(SEP_BLOCK)
                         for (int q = 0; q < NV; ++q)
 #pragma unroll
                             for (int e = 0; e < VEC; ++e) hs += wv[q * VEC + e] * (TA)v[u][q][e];
-                        acc[u] += wk[u] * hs;
+                        acc[u] += w[u][k] * hs;
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int y = y0 + yb + u * RG;
-                    const TA out = sep_normalise<TA>(acc[u], sumx * wys[yo[u]]);
-                    char *drow = (char *)kp.dst + (int64_t)blockIdx.y * kp.dst_batch_stride +
-                                 (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
-                    if (yb + u * RG < sp.th && y < kp.row1) store_dst<TO>(drow, x, (double)out);
+                    const TA out = sep_normalise<TA>(acc[u], sumx * w[u][MAXT]);
+                    if (yb + u * RG < ylim) store_dst<TO>(out_row, x, (double)out);
+                    out_row += (int64_t)RG * kp.dst_pitch;
                 }
             }
         }
@@ -356,7 +376,7 @@ cudaError_t launch_sep(const AaiKernelParams &kp, cudaStream_t stream) {
         sp.bw = ((int)ceil((TW - 1) * L) + MAXT + 3 + 2 * (TapVec<TI>::N - 1) + (align - 1) + align - 1) / align * align;
         sp.bh = (int)ceil((sp.th - 1) * L) + MAXT + 3;
         tile_bytes = ((size_t)sp.bw * sp.bh * esz + 127) / 128 * 128;
-        wgt_bytes = (((size_t)sp.th * MAXT + sp.th) * sizeof(TA) + (size_t)sp.th * sizeof(int) + 15) / 16 * 16;
+        wgt_bytes = sep_weight_bytes<TA, MAXT>(sp.th);
         smem = sp.stages * (tile_bytes + wgt_bytes) + 8 * sp.stages + 16;
         if (sp.bw <= 256 && sp.bh <= 256 && sp.bw >= MAXT && sp.bh >= MAXT && smem <= 112 * 1024) {
             found = true;
