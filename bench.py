@@ -443,8 +443,11 @@ def our_arm(args, cfg):
                     "hbm": {"achieved": alg_bytes / world / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "peak_source": hbm_src}}
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "latest.json")))
-        roofline["traffic"] = prof.get(f"cfg{args.config}", {}).get("dram_bytes_per_launch")
+        prof = json.load(open(os.path.join(ROOT, "profiles", "latest.json"))).get(f"cfg{args.config}", {})
+        traffic = prof.get("dram_bytes_per_launch")
+        if traffic is not None and "per" in prof:  # profiled per slice of a batched launch: scale to this rank's launch
+            traffic = int(traffic * cfg["batch"] / world)
+        roofline["traffic"] = traffic
     except Exception:
         pass
 
