@@ -502,6 +502,12 @@ def main():
                     help="N>1: every rank uploads its whole halo from the host instead of NVLink peer copies")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 (NCCL prints its version banner
+    # there under torchrun) are sent to stderr; the JSON line is written to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(json_fd, "w")
     if args.impl == "reference":
         return reference_arm(args, cfg)
     return our_arm(args, cfg)

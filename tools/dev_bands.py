@@ -1,0 +1,53 @@
+"""Developer tool: per-band kernel times of the row-band partition on ONE GPU (bands run one after another),
+to tune the partitioner's cost model.  python tools/dev_bands.py [--config 4] [--parts 8]"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import area_average_interpolation_b200 as aai
+from bench import CONFIGS
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", type=int, default=4)
+ap.add_argument("--parts", type=int, nargs="+", default=[8])
+ap.add_argument("--steps", type=int, default=20)
+args = ap.parse_args()
+cfg = CONFIGS[args.config]
+dev = torch.device("cuda:0")
+plan = aai.make_plan(cfg["w"], cfg["h"], 1.0, cfg["ratio"], cfg["iso"], cfg["angle"])
+tail = (cfg["ch"],) if cfg["ch"] > 1 else ()
+if cfg["dtype"] == "uint8":
+    src = torch.randint(0, 256, (cfg["h"], cfg["w"]) + tail, dtype=torch.uint8, device=dev)
+else:
+    src = torch.rand((cfg["h"], cfg["w"]) + tail, dtype=torch.float32, device=dev) * 4096
+dst = torch.empty((plan.dst_h, plan.dst_w) + tail, dtype=torch.float32, device=dev)
+si, di = aai.tensor_image(src), aai.tensor_image(dst)
+st = torch.cuda.current_stream().cuda_stream
+
+
+def timed(r0, r1):
+    for _ in range(3):
+        aai.run_device(plan, si, di, r0, r1, arith=aai.ARITH_F32, stream=st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        aai.run_device(plan, si, di, r0, r1, arith=aai.ARITH_F32, stream=st)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / args.steps
+
+
+whole = timed(0, plan.dst_h)
+print(f"whole canvas: {whole:.4f} ms")
+for n in args.parts:
+    b = aai.partition_rows(plan, n)
+    ts = [timed(b[k], b[k + 1]) for k in range(n)]
+    cov = [aai.covered_pixels(plan, b[k], b[k + 1]) for k in range(n)]
+    print(f"{n} bands: rows {[b[k + 1] - b[k] for k in range(n)]}")
+    print(f"   covered Mpx {[round(c / 1e6, 2) for c in cov]}")
+    print(f"   ms {[round(t, 4) for t in ts]}  max {max(ts):.4f}  sum {sum(ts):.4f}  ideal {whole / n:.4f}  "
+          f"speed-up {whole / max(ts):.2f}x")
