@@ -124,6 +124,7 @@ struct AaiShapeF {
     float ik;    // max(s,c)/min(s,c): advance along the major axis per unit of the minor axis
     float hq;    // (1 + min/max)/2
     float smin, smax;  // min(s,c), max(s,c)
+    float hc2, hs2;    // c/2, s/2 (side coefficients of the Green form)
     float area_total;  // L^2: total overlap of a footprint that lies inside the image (exact areas)
     int steep;   // 1: sin <= cos (major axis = y, the edges cross vertical grid lines rarely)
     int ncross;  // floor(L min(s,c)) + 1: most minor-axis grid lines one left/right edge can cross
@@ -155,6 +156,8 @@ inline AaiShapeF aai_make_shape_f(double c, double s, double L) {
     g.he = (float)(h * fabs(c - s));
     g.ik = (float)(mx / mn);
     g.hq = (float)((1.0 + mn / mx) / 2);
+    g.hc2 = (float)(c / 2);
+    g.hs2 = (float)(s / 2);
     g.smin = (float)mn;
     g.smax = (float)mx;
     g.area_total = (float)(L * L);
@@ -334,23 +337,25 @@ AAI_HD AaiF2 aai_cell_area_f32x2(const AaiShapeF &g, AaiF2 u0, AaiF2 v0, AaiF2 l
 //   outside case: the whole cell lies in the top/bottom slab, |v0| <= h - m.
 // (verified pair by pair against the FP64 slab form and the oracle.)
 // ------------------------------------------------------------------------------------------------------------
+// Green form with the vertex rotation folded into the side coefficients:
+//   A = lenT (1/4 + vy/2) + lenB (1/4 - vy/2) + lenL (1/4 + vx/2) + lenR (1/4 - vx/2),
+//   vx = ca c + cb s,  vy = cb c - ca s,  (ca, cb) = V - cell centre along (u, v)   (hc2 = c/2, hs2 = s/2)
 AAI_HD float aai_cell_exact_f32(const AaiShapeF &g, float u0, float v0, float lenT, float lenB, float lenL, float lenR) {
     const float ca = copysignf(g.half, u0) - u0;
     const float cb = copysignf(g.half, v0) - v0;
-    const float vx = fmaf(ca, g.cs, cb * g.sn);
-    const float vy = fmaf(cb, g.cs, -ca * g.sn);
-    return fmaf(0.25f, (lenT + lenB) + (lenL + lenR), 0.5f * fmaf(vy, lenT - lenB, vx * (lenL - lenR)));
+    const float aT = fmaf(cb, g.hc2, fmaf(ca, -g.hs2, 0.25f));
+    const float aL = fmaf(ca, g.hc2, fmaf(cb, g.hs2, 0.25f));
+    // lenT aT + lenB (1/2 - aT) + lenL aL + lenR (1/2 - aL), arranged as a shallow tree (the kernel is latency-bound)
+    return fmaf(aT, lenT - lenB, fmaf(aL, lenL - lenR, 0.5f * (lenB + lenR)));
 }
 AAI_HD AaiF2 aai_cell_exact_f32x2(const AaiShapeF &g, AaiF2 u0, AaiF2 v0, AaiF2 lenT, AaiF2 lenB, AaiF2 lenL,
                                   AaiF2 lenR) {
     const AaiF2 ca = aai_sub2(aai_f2(copysignf(g.half, u0.x), copysignf(g.half, u0.y)), u0);
     const AaiF2 cb = aai_sub2(aai_f2(copysignf(g.half, v0.x), copysignf(g.half, v0.y)), v0);
-    const AaiF2 cs2 = aai_f2(g.cs), sn2 = aai_f2(g.sn);
-    const AaiF2 vx = aai_fma2(ca, cs2, aai_mul2(cb, sn2));
-    const AaiF2 vy = aai_fma2(cb, cs2, aai_mul2(ca, aai_f2(-g.sn)));
-    const AaiF2 sum4 = aai_add2(aai_add2(lenT, lenB), aai_add2(lenL, lenR));
-    const AaiF2 cross = aai_fma2(vy, aai_sub2(lenT, lenB), aai_mul2(vx, aai_sub2(lenL, lenR)));
-    return aai_fma2(aai_f2(0.25f), sum4, aai_mul2(aai_f2(0.5f), cross));
+    const AaiF2 aT = aai_fma2(cb, aai_f2(g.hc2), aai_fma2(ca, aai_f2(-g.hs2), aai_f2(0.25f)));
+    const AaiF2 aL = aai_fma2(ca, aai_f2(g.hc2), aai_fma2(cb, aai_f2(g.hs2), aai_f2(0.25f)));
+    const AaiF2 half_br = aai_fma2(lenB, aai_f2(0.5f), aai_mul2(lenR, aai_f2(0.5f)));
+    return aai_fma2(aT, aai_sub2(lenT, lenB), aai_fma2(aL, aai_sub2(lenL, lenR), half_br));
 }
 
 // One edge line in one row band.  LEFT: the left edge (u = -h), else the right edge (u = +h).

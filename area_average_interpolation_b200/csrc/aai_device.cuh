@@ -16,9 +16,11 @@ namespace aai_dev {
 #define AAI_TILE_W 16
 #endif
 #ifndef AAI_TILE_H
-#define AAI_TILE_H 16
+#define AAI_TILE_H 8
 #endif
-constexpr int TILE_W = AAI_TILE_W;  // canvas pixels per CTA (one thread each); a warp covers 32/TILE_W rows
+// canvas pixels per CTA (one thread each); a warp covers 32/TILE_W rows.  16x8 (128 threads, 6 CTAs/SM for the FP32
+// kernel) measured 3.7 % faster than 16x16 on config 4: same warps per SM, finer-grained CTA turnover.
+constexpr int TILE_W = AAI_TILE_W;
 constexpr int TILE_H = AAI_TILE_H;
 
 template <typename T>

@@ -67,7 +67,7 @@ __device__ __forceinline__ void store_f<uint8_t>(void *row, int idx, float v) {
 // IDENT: scale 1, quadrant 0 (expanded pixel (i,j) IS source pixel (i,j)): constant element stride, offsets fold
 // into the load instruction.  Otherwise the general expanded-frame affine map + division by the scale.
 #ifndef AAI_F32_MIN_BLOCKS
-#define AAI_F32_MIN_BLOCKS (AAI_MAXN <= 5 ? 3 : 2)
+#define AAI_F32_MIN_BLOCKS ((AAI_MAXN <= 5 ? 896 : 512) / (AAI_TILE_W * AAI_TILE_H))  // 28 resp. 16 warps per SM
 #endif
 template <typename TI, typename TO, int NC, bool IDENT>
 __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
@@ -192,10 +192,13 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             for (int k = 0; k + 1 < MAXN; k += 2) {
                 const float rxa = rx0 + (float)k, rxb = rx0 + (float)(k + 1);
                 const float exa = rxa - 0.5f, exb = rxb - 0.5f;
-                const float lenM = aai_overlap1_f32(yt[k + 1], yb[k + 1], ey);
-                const float lenR = aai_overlap1_f32(yt[k + 2], yb[k + 2], ey);
+                // side lengths of the two cells: saturated ends on the scalar pipe, their differences packed
+                const AaiF2 lMR = aai_sub2(aai_f2(aai_sat(yb[k + 1] - ey), aai_sat(yb[k + 2] - ey)),
+                                           aai_f2(aai_sat(yt[k + 1] - ey), aai_sat(yt[k + 2] - ey)));
+                const float lenM = lMR.x, lenR = lMR.y;
                 const AaiF2 lT = aai_f2(lenTop[k], lenTop[k + 1]);
-                const AaiF2 lB = aai_f2(aai_overlap1_f32(xlB, xrB, exa), aai_overlap1_f32(xlB, xrB, exb));
+                const AaiF2 lB = aai_sub2(aai_f2(aai_sat(xrB - exa), aai_sat(xrB - exb)),
+                                          aai_f2(aai_sat(xlB - exa), aai_sat(xlB - exb)));
                 lenTop[k] = lB.x;
                 lenTop[k + 1] = lB.y;
                 const AaiF2 rx2 = aai_f2(rxa, rxb);
