@@ -233,26 +233,36 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         // edge.
         if (kp.quirk) {
             const float g0m = g.steep ? e0 : t0, g0M = g.steep ? t0 : e0;
-            auto fix = [&](int mi, int Mi, float d) {  // cell (minor index, major index) += d
+            // the two cells of a crossing are neighbours along the minor axis: one address, one stride.  Branch-free: an
+            // event that does not apply has d = 0 (its cells are clamped into the footprint's range and contribute 0).
+            const int64_t minor_stride = IDENT ? (g.steep ? (int64_t)ESZ : kp.src_pitch) : 0;
+            auto fix2 = [&](int mi, int Mi, float d_before, float d_after) {
+                const int mlim = (g.steep ? ncols : nrows) - 2, Mlim = (g.steep ? nrows : ncols) - 1;
+                mi = max(0, min(mi, mlim));
+                Mi = max(0, min(Mi, Mlim));
                 const int k = g.steep ? mi : Mi, r = g.steep ? Mi : mi;
-                if (d != 0.0f && (unsigned)k < (unsigned)ncols && (unsigned)r < (unsigned)nrows) {
-                    const char *p = IDENT ? rowp0 + (int64_t)r * kp.src_pitch + (int64_t)k * ESZ
-                                          : (const char *)kp.src + row_off(jy0 + r) + col_off(ix0 + k);
-                    sumA += d;
+                const char *p0, *p1;
+                if (IDENT) {
+                    p0 = rowp0 + (int64_t)r * kp.src_pitch + (int64_t)k * ESZ;
+                    p1 = p0 + minor_stride;
+                } else {
+                    p0 = (const char *)kp.src + row_off(jy0 + r) + col_off(ix0 + k);
+                    p1 = (const char *)kp.src + row_off(jy0 + r + (g.steep ? 0 : 1)) + col_off(ix0 + k + (g.steep ? 1 : 0));
+                }
+                sumA += d_before + d_after;
 #pragma unroll
-                    for (int ch = 0; ch < NC; ++ch)
-                        acc[ch] = fmaf(LoadF<TI>::get(p + ch * (int)sizeof(TI)), d, acc[ch]);
+                for (int ch = 0; ch < NC; ++ch) {
+                    acc[ch] = fmaf(LoadF<TI>::get(p0 + ch * (int)sizeof(TI)), d_before, acc[ch]);
+                    acc[ch] = fmaf(LoadF<TI>::get(p1 + ch * (int)sizeof(TI)), d_after, acc[ch]);
                 }
             };
             for (int q = 0; q < g.ncross; ++q) {
                 int mi, Mi;
                 float db, da;
                 aai_edge_quirk_f32<true>(g, g0m, g0M, q, mi, Mi, db, da, worst);
-                fix(mi, Mi, db);
-                fix(mi + 1, Mi, da);
+                fix2(mi, Mi, db, da);
                 aai_edge_quirk_f32<false>(g, g0m, g0M, q, mi, Mi, db, da, worst);
-                fix(mi, Mi, db);
-                fix(mi + 1, Mi, da);
+                fix2(mi, Mi, db, da);
             }
         }
         // guard band of the quirk decision -> FP64
