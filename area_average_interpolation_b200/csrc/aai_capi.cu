@@ -345,7 +345,7 @@ int aai_run_device(const aai_plan *plan, int mode, int arith, const aai_image *s
     kp.quirk = mode == AAI_MODE_AREA_AVERAGE_EXACT ? 0 : 1;
     int e;
     if (mode == AAI_MODE_FAST)
-        e = aai_launch_fast(kp, src->dtype, dst->dtype, stream);
+        e = aai_launch_fast(kp, arith, src->dtype, dst->dtype, stream);
     else if (plan->axis_aligned)
         e = aai_launch_separable(kp, arith, src->dtype, dst->dtype, stream);
     else

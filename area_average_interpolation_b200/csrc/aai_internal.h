@@ -47,7 +47,7 @@ AaiKernelParams aai_make_kernel_params(const aai_plan &plan, const aai_image &sr
 // kernel launchers (aai_kernels.cu); return the cudaError_t of the launch as int
 int aai_launch_overlap(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_separable(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);
-int aai_launch_fast(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
+int aai_launch_fast(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_expand(const AaiKernelParams &kp, int elem_bytes, void *stream);
 // aai_kernels_sep.cu: TMA-staged separable kernel; returns cudaErrorNotSupported when its fast path does not apply
 int aai_launch_separable_tma(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);

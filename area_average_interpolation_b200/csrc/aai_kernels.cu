@@ -91,11 +91,9 @@ __global__ void __launch_bounds__(TILE_W *TILE_H)
 // ------------------------------------------------------------------------------------------------------------
 // Fast mode (Source.cpp:866-907): unweighted mean of the expanded pixels whose CENTRE lies in the footprint.
 // ------------------------------------------------------------------------------------------------------------
-template <typename TI, typename TO, int NC>
-__global__ void __launch_bounds__(TILE_W *TILE_H) fast_kernel(const __grid_constant__ AaiKernelParams kp) {
-    const int x = blockIdx.x * TILE_W + threadIdx.x;
-    const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
-    if (x >= kp.dst_w || y >= kp.row1) return;
+// FP64 evaluation of one canvas pixel (also the precision fallback of the FP32 fast kernel)
+template <typename TI, int NC>
+__device__ __forceinline__ void pixel_fast_f64(const AaiKernelParams &kp, int x, int y, int &count, double (&acc)[NC]) {
     double cx, cy;
     pixel_centre(kp, x, y, cx, cy);
     int wx0, wx1, wy0, wy1;
@@ -103,8 +101,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H) fast_kernel(const __grid_const
     const double ext = kp.hb + 1e-6;
     const int ix0 = max(wx0, __double2int_ru(cx - ext)), ix1 = min(wx1, __double2int_rd(cx + ext));
     const int jy0 = max(wy0, __double2int_ru(cy - ext)), jy1 = min(wy1, __double2int_rd(cy + ext));
-    int count = 0;
-    double acc[NC];
+    count = 0;
 #pragma unroll
     for (int ch = 0; ch < NC; ++ch) acc[ch] = 0.0;
     for (int j = jy0; j <= jy1; ++j) {
@@ -123,9 +120,87 @@ __global__ void __launch_bounds__(TILE_W *TILE_H) fast_kernel(const __grid_const
             }
         }
     }
+}
+
+template <typename TI, typename TO, int NC>
+__global__ void __launch_bounds__(TILE_W *TILE_H) fast_kernel(const __grid_constant__ AaiKernelParams kp) {
+    const int x = blockIdx.x * TILE_W + threadIdx.x;
+    const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
+    if (x >= kp.dst_w || y >= kp.row1) return;
+    int count;
+    double acc[NC];
+    pixel_fast_f64<TI, NC>(kp, x, y, count, acc);
     char *drow = (char *)kp.dst + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
 #pragma unroll
     for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, count > 0 ? acc[ch] / (double)count : 0.0);
+}
+
+// FP32 arithmetic for float / 8-bit images.  The inside test is a discontinuous decision, so -- as in the FP32 overlap
+// kernel -- the footprint centre is split into a lattice point and an FP32 fraction, the smallest margin of the decisive
+// comparisons is tracked, and a pixel with a margin inside the guard band is redone in FP64 (pixel_fast_f64).
+template <typename TI, typename TO, int NC>
+__global__ void __launch_bounds__(TILE_W *TILE_H) fast_kernel_f32(const __grid_constant__ AaiKernelParams kp) {
+    const int x = blockIdx.x * TILE_W + threadIdx.x;
+    const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
+    if (x >= kp.dst_w || y >= kp.row1) return;
+    const double cx = fma((double)x, kp.aff_xx, fma((double)y, kp.aff_xy, kp.aff_x0));
+    const double cy = fma((double)x, kp.aff_yx, fma((double)y, kp.aff_yy, kp.aff_y0));
+    const int irx = __double2int_rn(cx), iry = __double2int_rn(cy);
+    const float fx = (float)(cx - (double)irx), fy = (float)(cy - (double)iry);
+    // cells whose centre can lie in the footprint: |i - cx| <= h(c+s) (with an FP32 safety margin), inside the image
+    const float ext = kp.shapef.hb + 4e-6f;
+    const int ix0 = max(0, irx + __float2int_ru(fx - ext)), ix1 = min(kp.mod_w - 1, irx + __float2int_rd(fx + ext));
+    const int jy0 = max(0, iry + __float2int_ru(fy - ext)), jy1 = min(kp.mod_h - 1, iry + __float2int_rd(fy + ext));
+    const AaiShapeF &g = kp.shapef;
+    const float tau = 4e-6f;
+    float count = 0.0f, acc[NC], worst = 1.0f;
+#pragma unroll
+    for (int ch = 0; ch < NC; ++ch) acc[ch] = 0.0f;
+    const bool ident = kp.scale == 1 && kp.quadrant == 0;
+    constexpr int ESZ = (int)sizeof(TI) * NC;
+    const float rx0 = (float)(ix0 - irx) - fx;
+    for (int j = jy0; j <= jy1; ++j) {
+        const float ry = (float)(j - iry) - fy;
+        const float ur = -ry * g.sn, vr = ry * g.cs;
+        const char *rowp = (const char *)kp.src + (int64_t)(j - kp.src_y0) * kp.src_pitch + (int64_t)ix0 * ESZ;  // ident only
+        float rx = rx0;
+        for (int i = ix0; i <= ix1; ++i, rx += 1.0f, rowp += ESZ) {
+            const float mu = g.half - fabsf(fmaf(rx, g.cs, ur));
+            const float mv = g.half - fabsf(fmaf(rx, g.sn, vr));
+            // margins of the comparisons that decide (the other coordinate is not clearly outside)
+            if (mv > -tau) worst = fminf(worst, fabsf(mu));
+            if (mu > -tau) worst = fminf(worst, fabsf(mv));
+            if (mu >= 0.0f && mv >= 0.0f) {  // closed point-in-square (837-864)
+                const char *p = rowp;
+                if (!ident) {
+                    int sx, sy;
+                    mod_to_src(kp, i, j, sx, sy);
+                    p = (const char *)kp.src + (int64_t)(sy - kp.src_y0) * kp.src_pitch + (int64_t)sx * ESZ;
+                }
+                count += 1.0f;
+#pragma unroll
+                for (int ch = 0; ch < NC; ++ch) {
+                    float v;
+                    if (sizeof(TI) == 8) v = (float)__ldg((const double *)p + ch);
+                    else if (sizeof(TI) == 4) v = __ldg((const float *)p + ch);
+                    else v = (float)__ldg((const uint8_t *)p + ch);
+                    acc[ch] += v;
+                }
+            }
+        }
+    }
+    char *drow = (char *)kp.dst + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
+    if (worst < tau) {  // a centre within the guard band of a footprint edge: FP64 decides
+        int c64;
+        double a64[NC];
+        pixel_fast_f64<TI, NC>(kp, x, y, c64, a64);
+#pragma unroll
+        for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, c64 > 0 ? a64[ch] / (double)c64 : 0.0);
+    } else {
+        const float inv = count > 0.0f ? 1.0f / count : 0.0f;
+#pragma unroll
+        for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, (double)(acc[ch] * inv));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -143,7 +218,7 @@ __global__ void __launch_bounds__(256) expand_kernel(const __grid_constant__ Aai
     for (int ch = 0; ch < kp.channels; ++ch) drow[mx * kp.channels + ch] = srow[sx * kp.channels + ch];
 }
 
-enum KernelKind { K_OVERLAP, K_SEPARABLE, K_FAST };
+enum KernelKind { K_OVERLAP, K_SEPARABLE, K_FAST, K_FAST_F32 };
 
 template <typename TI, typename TO, int NC>
 cudaError_t launch_typed(KernelKind kind, const AaiKernelParams &kp, cudaStream_t stream) {
@@ -155,6 +230,7 @@ cudaError_t launch_typed(KernelKind kind, const AaiKernelParams &kp, cudaStream_
         case K_OVERLAP: overlap_kernel_f64<TI, TO, NC><<<grid, block, 0, stream>>>(kp); break;
         case K_SEPARABLE: separable_kernel_f64<TI, TO, NC><<<grid, block, 0, stream>>>(kp); break;
         case K_FAST: fast_kernel<TI, TO, NC><<<grid, block, 0, stream>>>(kp); break;
+        case K_FAST_F32: fast_kernel_f32<TI, TO, NC><<<grid, block, 0, stream>>>(kp); break;
     }
     return cudaGetLastError();
 }
@@ -221,6 +297,9 @@ int aai_launch_expand(const AaiKernelParams &kp, int elem_bytes, void *stream) {
     return (int)cudaGetLastError();
 }
 
-int aai_launch_fast(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream) {
-    return (int)launch_any(K_FAST, kp, src_dtype, dst_dtype, (cudaStream_t)stream);
+int aai_launch_fast(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream) {
+    // FP32 arithmetic on request for float / 8-bit sources (the mean of 8-byte doubles stays in FP64)
+    const bool f32 = arith == AAI_ARITH_F32 && src_dtype != AAI_F64 && dst_dtype != AAI_F64 &&
+                     (uint64_t)(kp.mod_w > kp.mod_h ? kp.mod_w : kp.mod_h) < (1u << 30);
+    return (int)launch_any(f32 ? K_FAST_F32 : K_FAST, kp, src_dtype, dst_dtype, (cudaStream_t)stream);
 }
