@@ -238,7 +238,9 @@ AAI_HD float aai_cell_area_f32(const AaiShapeF &g, float u0, float v0, float len
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Packed variant: two horizontally adjacent cells per call on Blackwell's packed FP32 pipe (FFMA2 / FMUL2 / FADD2,
+// Packed variant of the per-cell decision form (CPU cross-check only since the kernel moved to exact areas + edge
+// events; the kernel's packed routine is aai_cell_exact_f32x2 below): two horizontally adjacent cells per call on
+// Blackwell's packed FP32 pipe (FFMA2 / FMUL2 / FADD2,
 // `fma.rn.f32x2` -- sm_100a).  The kernel is instruction-issue bound, and every multiply/add of the cell math is
 // independent between cells, so two cells share one instruction.  Same arithmetic, operation by operation, as
 // aai_cell_area_f32 (the host build of this header evaluates the two lanes with scalar fmaf).
@@ -321,7 +323,8 @@ AAI_HD AaiF2 aai_cell_area_f32x2(const AaiShapeF &g, AaiF2 u0, AaiF2 v0, AaiF2 l
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Row formulation of the quirk (what the FP32 kernel runs): exact areas for every cell (Green form, no decision),
+// Row formulation of the quirk (the kernel's previous formulation, kept as an independent cross-check of the edge
+// formulation below in the CPU tests -- no kernel calls it any more): exact areas for every cell (Green form, no decision),
 // plus, per row band and per left/right edge line, at most two area CORRECTIONS.
 //
 // A left/right edge line has direction (s,c) (down-right).  In a row band it enters through the band's top at
@@ -401,7 +404,7 @@ AAI_HD void aai_row_quirk_f32(const AaiShapeF &g, float z, float yT, float rx0, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Edge formulation of the quirk (what the FP32 kernel runs now): the corrected cells of the row formulation above
+// Edge formulation of the quirk (what the FP32 kernel runs): the corrected cells of the row formulation above
 // are exactly the cells in which a left/right edge changes from "advancing along its major axis" to "stepping over a
 // minor-axis grid line" -- one pair of cells per minor-axis grid line the edge SEGMENT crosses, at most
 // floor(L min(s,c)) + 1 of them -- so they are enumerated per edge instead of being searched for in every row.
