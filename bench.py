@@ -42,11 +42,11 @@ CONFIGS = {
     1: dict(label="cfg1: 512x512 u8 grayscale, 0.5x, 0 deg", w=512, h=512, dtype="uint8", ch=1, ratio=0.5,
             angle=0.0, iso=(256.0, 256.0), batch=1, replica=512, baseline_replica=512),
     2: dict(label="cfg2: 2048x2048 u8 grayscale, 0.37x, 30 deg", w=2048, h=2048, dtype="uint8", ch=1, ratio=0.37,
-            angle=30.0, iso=(1024.0, 1024.0), batch=1, replica=512, baseline_replica=1024),
+            angle=30.0, iso=(1024.0, 1024.0), batch=1, replica=512, baseline_replica=2048),
     3: dict(label="cfg3: 8192x8192 RGB u8, 1.7x, 45 deg", w=8192, h=8192, dtype="uint8", ch=3, ratio=1.7, angle=45.0,
-            iso=(4095.5, 4095.5), batch=1, replica=128, baseline_replica=256),
+            iso=(4095.5, 4095.5), batch=1, replica=128, baseline_replica=384),
     4: dict(label="cfg4: 16384x16384 float32, 0.37x, 17.3 deg", w=16384, h=16384, dtype="float32", ch=1, ratio=0.37,
-            angle=17.3, iso=(8192.0, 8192.0), batch=1, replica=512, baseline_replica=1024),
+            angle=17.3, iso=(8192.0, 8192.0), batch=1, replica=512, baseline_replica=2048),
     5: dict(label="cfg5: 256 x 4096x4096 float32, 0.5x, 0 deg", w=4096, h=4096, dtype="float32", ch=1, ratio=0.5,
             angle=0.0, iso=(2048.0, 2048.0), batch=256, replica=512, baseline_replica=1024),
 }
