@@ -274,6 +274,13 @@ AAI_HD AaiF2 aai_mul2(AaiF2 a, AaiF2 b) { return aai_f2(a.x * b.x, a.y * b.y); }
 AAI_HD AaiF2 aai_add2(AaiF2 a, AaiF2 b) { return aai_f2(a.x + b.x, a.y + b.y); }
 #endif
 AAI_HD AaiF2 aai_sub2(AaiF2 a, AaiF2 b) { return aai_fma2(b, aai_f2(-1.0f), a); }  // a - b as one FFMA2
+// chords of the footprint on two vertical grid lines at once (same arithmetic as aai_chord_v_f32, lane by lane)
+AAI_HD void aai_chord_v_f32x2(const AaiShapeF &g, AaiF2 tx, AaiF2 &yt, AaiF2 &yb) {
+    const AaiF2 a = aai_fma2(tx, aai_f2(g.k_cs), aai_f2(-g.k_hs)), b = aai_fma2(tx, aai_f2(-g.k_sc), aai_f2(-g.k_hc));
+    const AaiF2 c = aai_fma2(tx, aai_f2(g.k_cs), aai_f2(g.k_hs)), d = aai_fma2(tx, aai_f2(-g.k_sc), aai_f2(g.k_hc));
+    yt = aai_f2(fmaxf(a.x, b.x), fmaxf(a.y, b.y));
+    yb = aai_f2(fmaxf(fminf(c.x, d.x), yt.x), fmaxf(fminf(c.y, d.y), yt.y));
+}
 AAI_HD float aai_flip(float v, float sign_of) {  // v with its sign flipped when sign_of is negative (one LOP3)
 #if defined(__CUDA_ARCH__)
     return __int_as_float(__float_as_int(v) ^ (__float_as_int(sign_of) & 0x80000000));

@@ -108,7 +108,15 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         const float rx0 = (float)(ix0 - irx) - fx;
         float yt[MAXN + 1], yb[MAXN + 1];
 #pragma unroll
-        for (int k = 0; k <= MAXN; ++k) aai_chord_v_f32(g, rx0 + ((float)k - 0.5f), yt[k], yb[k]);
+        for (int k = 0; k + 1 <= MAXN; k += 2) {  // two grid lines per packed instruction
+            AaiF2 t2, b2;
+            aai_chord_v_f32x2(g, aai_f2(rx0 + ((float)k - 0.5f), rx0 + ((float)k + 0.5f)), t2, b2);
+            yt[k] = t2.x;
+            yt[k + 1] = t2.y;
+            yb[k] = b2.x;
+            yb[k + 1] = b2.y;
+        }
+        if ((MAXN + 1) & 1) aai_chord_v_f32(g, rx0 + ((float)MAXN - 0.5f), yt[MAXN], yb[MAXN]);
         float xlT, xrT;  // chord of the footprint on the row's top grid line
         const float t0 = ((float)dj0 - fy) - 0.5f;  // top of row 0
         aai_chord_h_f32(g, t0, xlT, xrT);
