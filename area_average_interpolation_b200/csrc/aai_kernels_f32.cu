@@ -69,9 +69,17 @@ __device__ __forceinline__ void store_f<uint8_t>(void *row, int idx, float v) {
 #ifndef AAI_F32_MIN_BLOCKS
 #define AAI_F32_MIN_BLOCKS ((AAI_MAXN <= 5 ? 896 : 512) / (AAI_TILE_W * AAI_TILE_H))  // 28 resp. 16 warps per SM
 #endif
-template <typename TI, typename TO, int NC, bool IDENT>
+// ADDR: how a cell finds its source value.
+//   ADDR_GENERAL  expanded + quadrant-rotated frame, separable byte offset col_off(i) + row_off(j)
+//   ADDR_IDENT    scale 1, quadrant 0: expanded pixel (i,j) IS source pixel (i,j), offsets fold into the loads
+//   ADDR_GROUPED  general frame with scale >= MAXN-1 (upscaling): the <= MAXN x MAXN cells of a footprint fall into at
+//                 most 2 x 2 source pixels, so the areas (and the quirk corrections) are summed per source pixel in
+//                 four registers and each source pixel is loaded ONCE per canvas pixel instead of once per cell
+enum { ADDR_GENERAL = 0, ADDR_IDENT = 1, ADDR_GROUPED = 2 };
+template <typename TI, typename TO, int NC, int ADDR>
 __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
     overlap_kernel_f32(const __grid_constant__ AaiKernelParams kp) {
+    constexpr bool IDENT = ADDR == ADDR_IDENT, GROUPED = ADDR == ADDR_GROUPED;
     const int x = blockIdx.x * TILE_W + threadIdx.x;
     const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
     if (x >= kp.dst_w || y >= kp.row1) return;
@@ -144,6 +152,16 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
 #pragma unroll
             for (int k = 0; k < MAXN; ++k) coff[k] = col_off(ix0 + min(k, ncols - 1));
         }
+        // GROUPED: column k belongs to the first source column (group A) or to the second one (group B); rows likewise
+        // (top / bottom); W[row group][column group] = total weight of the source pixel
+        unsigned colA = 0, rowTop = 0;
+        float W00 = 0.0f, W01 = 0.0f, W10 = 0.0f, W11 = 0.0f;
+        int64_t roff0 = 0;
+        if (GROUPED) {
+#pragma unroll
+            for (int k = 0; k < MAXN; ++k) colA |= (coff[k] == coff[0] ? 1u : 0u) << k;
+            roff0 = row_off(jy0);
+        }
         // lengths of the cells' top sides inside the footprint: the previous row's bottom sides
         float lenTop[MAXN];
 #pragma unroll
@@ -151,7 +169,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         // Source values are fetched one row ahead of their use (the loads of row r+1 are in flight while the areas of
         // row r are computed): the accumulate at the end of a row never waits for its own row's loads.
         // (Single-channel kernels only: three channels would need 30 staging registers.)
-        constexpr bool PREFETCH = NC == 1;
+        constexpr bool PREFETCH = NC == 1 && !GROUPED;
         float cur[MAXN][NC];
         auto fetch = [&](int r, float (&v)[MAXN][NC]) {
             if (IDENT)
@@ -175,8 +193,14 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             float nxt[MAXN][NC];
             if (PREFETCH) {
                 if (r + 1 < nrows) fetch(r + 1, nxt);
-            } else {
+            } else if (!GROUPED) {
                 rowp = IDENT ? rowp0 + (int64_t)r * kp.src_pitch : (const char *)kp.src + row_off(jy0 + r);
+            }
+            float rowA = 0.0f, rowB = 0.0f;  // GROUPED: this row's area in the first / second source column
+            bool top = true;
+            if (GROUPED) {
+                top = row_off(jy0 + r) == roff0;
+                rowTop |= (top ? 1u : 0u) << r;
             }
             const float ry = (float)(dj0 + r) - fy;
             float xlB, xrB;
@@ -185,7 +209,12 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             float lenL = aai_overlap1_f32(yt[0], yb[0], ey);
             const float ur = -ry * g.sn, vr = ry * g.cs;
             auto take = [&](int k, float area) {
-                if (PREFETCH) {
+                if (GROUPED) {  // cells beyond ncols have area exactly 0
+                    if ((colA >> k) & 1u)
+                        rowA += area;
+                    else
+                        rowB += area;
+                } else if (PREFETCH) {
 #pragma unroll
                     for (int ch = 0; ch < NC; ++ch) acc[ch] = fmaf(cur[k][ch], area, acc[ch]);
                 } else if (k < ncols) {  // load at the point of use
@@ -228,6 +257,12 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 const float area = aai_cell_exact_f32(g, u0, v0, lenT, lenB, lenL, lenR);
                 take(k, area);
             }
+            if (GROUPED) {
+                W00 += top ? rowA : 0.0f;
+                W01 += top ? rowB : 0.0f;
+                W10 += top ? 0.0f : rowA;
+                W11 += top ? 0.0f : rowB;
+            }
             if (PREFETCH) {
 #pragma unroll
                 for (int k = 0; k < MAXN; ++k)
@@ -249,6 +284,19 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 mi = max(0, min(mi, mlim));
                 Mi = max(0, min(Mi, Mlim));
                 const int k = g.steep ? mi : Mi, r = g.steep ? Mi : mi;
+                if (GROUPED) {  // corrections go to the weights of the cells' source pixels: no loads here
+                    auto add_w = [&](int kk, int rr, float d) {
+                        const bool a = (colA >> kk) & 1u, t = (rowTop >> rr) & 1u;
+                        W00 += (t && a) ? d : 0.0f;
+                        W01 += (t && !a) ? d : 0.0f;
+                        W10 += (!t && a) ? d : 0.0f;
+                        W11 += (!t && !a) ? d : 0.0f;
+                    };
+                    add_w(k, r, d_before);
+                    add_w(k + (g.steep ? 1 : 0), r + (g.steep ? 0 : 1), d_after);
+                    sumA += d_before + d_after;
+                    return;
+                }
                 const char *p0, *p1;
                 if (IDENT) {
                     p0 = rowp0 + (int64_t)r * kp.src_pitch + (int64_t)k * ESZ;
@@ -271,6 +319,19 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 fix2(mi, Mi, db, da);
                 aai_edge_quirk_f32<false>(g, g0m, g0M, q, mi, Mi, db, da, worst);
                 fix2(mi, Mi, db, da);
+            }
+        }
+        if (GROUPED) {  // the (at most) four source pixels, once each
+            const int64_t roffL = row_off(jy1), coffL = coff[MAXN - 1];
+            const char *base = (const char *)kp.src;
+            const char *p00 = base + roff0 + coff[0], *p01 = base + roff0 + coffL;
+            const char *p10 = base + roffL + coff[0], *p11 = base + roffL + coffL;
+#pragma unroll
+            for (int ch = 0; ch < NC; ++ch) {
+                const int o = ch * (int)sizeof(TI);
+                acc[ch] = fmaf(LoadF<TI>::get(p00 + o), W00,
+                               fmaf(LoadF<TI>::get(p01 + o), W01,
+                                    fmaf(LoadF<TI>::get(p10 + o), W10, LoadF<TI>::get(p11 + o) * W11)));
             }
         }
         // guard band of the quirk decision -> FP64
@@ -300,9 +361,11 @@ cudaError_t launch3(const AaiKernelParams &kp, cudaStream_t stream) {
     dim3 block(TILE_W, TILE_H);
     dim3 grid((kp.dst_w + TILE_W - 1) / TILE_W, (rows + TILE_H - 1) / TILE_H);
     if (kp.scale == 1 && kp.quadrant == 0)
-        overlap_kernel_f32<TI, TO, NC, true><<<grid, block, 0, stream>>>(kp);
+        overlap_kernel_f32<TI, TO, NC, ADDR_IDENT><<<grid, block, 0, stream>>>(kp);
+    else if (MAXN == 4 && kp.scale >= MAXN - 1)
+        overlap_kernel_f32<TI, TO, NC, (MAXN == 4 ? ADDR_GROUPED : ADDR_GENERAL)><<<grid, block, 0, stream>>>(kp);
     else
-        overlap_kernel_f32<TI, TO, NC, false><<<grid, block, 0, stream>>>(kp);
+        overlap_kernel_f32<TI, TO, NC, ADDR_GENERAL><<<grid, block, 0, stream>>>(kp);
     return cudaGetLastError();
 }
 template <typename TI, typename TO>
