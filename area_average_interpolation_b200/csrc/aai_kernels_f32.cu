@@ -148,19 +148,25 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                            : (div_s(kp.e_ayj * j + kp.e_ay0) - kp.src_y0) * kp.src_pitch;
         };
         int64_t coff[MAXN];
-        if (!IDENT) {
+        if (!IDENT && !GROUPED) {
 #pragma unroll
             for (int k = 0; k < MAXN; ++k) coff[k] = col_off(ix0 + min(k, ncols - 1));
         }
-        // GROUPED: column k belongs to the first source column (group A) or to the second one (group B); rows likewise
-        // (top / bottom); W[row group][column group] = total weight of the source pixel
+        // GROUPED: column k belongs to the first source column (group A, bit k of colA) or to the second one (group B);
+        // rows likewise (rowTop); W[row group][column group] = total weight of the source pixel.  Along an axis the
+        // expanded coordinate e moves by +-1 per cell, so the first group holds S - e mod S (resp. e mod S + 1) cells.
         unsigned colA = 0, rowTop = 0;
         float W00 = 0.0f, W01 = 0.0f, W10 = 0.0f, W11 = 0.0f;
-        int64_t roff0 = 0;
         if (GROUPED) {
-#pragma unroll
-            for (int k = 0; k < MAXN; ++k) colA |= (coff[k] == coff[0] ? 1u : 0u) << k;
-            roff0 = row_off(jy0);
+            auto first_group = [&](int e, int step) -> unsigned {  // mask of the cells sharing the first cell's source
+                const int rem = e - (int)div_s(e) * kp.scale;
+                const int n = step > 0 ? kp.scale - rem : rem + 1;
+                return n >= MAXN ? (1u << MAXN) - 1u : (1u << n) - 1u;
+            };
+            const int ac = swapped ? kp.e_ayi : kp.e_axi, ec0 = swapped ? kp.e_ay0 : kp.e_ax0;
+            const int ar = swapped ? kp.e_axj : kp.e_ayj, er0 = swapped ? kp.e_ax0 : kp.e_ay0;
+            colA = first_group(ac * ix0 + ec0, ac);
+            rowTop = first_group(ar * jy0 + er0, ar);
         }
         // lengths of the cells' top sides inside the footprint: the previous row's bottom sides
         float lenTop[MAXN];
@@ -197,11 +203,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 rowp = IDENT ? rowp0 + (int64_t)r * kp.src_pitch : (const char *)kp.src + row_off(jy0 + r);
             }
             float rowA = 0.0f, rowB = 0.0f;  // GROUPED: this row's area in the first / second source column
-            bool top = true;
-            if (GROUPED) {
-                top = row_off(jy0 + r) == roff0;
-                rowTop |= (top ? 1u : 0u) << r;
-            }
+            const bool top = (rowTop >> r) & 1u;
             const float ry = (float)(dj0 + r) - fy;
             float xlB, xrB;
             aai_chord_h_f32(g, ry + 0.5f, xlB, xrB);
@@ -322,10 +324,10 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             }
         }
         if (GROUPED) {  // the (at most) four source pixels, once each
-            const int64_t roffL = row_off(jy1), coffL = coff[MAXN - 1];
+            const int64_t roff0 = row_off(jy0), roffL = row_off(jy1), coff0 = col_off(ix0), coffL = col_off(ix1);
             const char *base = (const char *)kp.src;
-            const char *p00 = base + roff0 + coff[0], *p01 = base + roff0 + coffL;
-            const char *p10 = base + roffL + coff[0], *p11 = base + roffL + coffL;
+            const char *p00 = base + roff0 + coff0, *p01 = base + roff0 + coffL;
+            const char *p10 = base + roffL + coff0, *p11 = base + roffL + coffL;
 #pragma unroll
             for (int ch = 0; ch < NC; ++ch) {
                 const int o = ch * (int)sizeof(TI);
