@@ -476,6 +476,44 @@ AAI_HD void aai_edge_quirk_f32(const AaiShapeF &g, float g0m, float g0M, int n, 
     }
 }
 
+// Both edges of one crossing index at once on the packed FP32 pipe: lane .x = ALPHA, lane .y = BETA.  Same arithmetic as
+// aai_edge_quirk_f32, operation by operation (the CPU tests compare the two bit for bit); the kernel is issue-bound
+// and the two edges' computations are independent, so they share instructions.
+AAI_HD void aai_edge_quirk_pair_f32(const AaiShapeF &g, float g0m, float g0M, int n, int (&mi)[2], int (&Mi)[2],
+                                    float (&d_before)[2], float (&d_after)[2], float &worst) {
+    const AaiF2 qA = aai_f2(-g.hb, g.he), qB = aai_f2(-g.he, g.hb), pA = aai_f2(-g.he, -g.hb);
+    const float span = g.hb + g.he;
+    const AaiF2 t = aai_sub2(qA, aai_f2(g0m));
+    const AaiF2 icf = aai_add2(aai_f2(ceilf(t.x), ceilf(t.y)), aai_f2((float)n));
+    const AaiF2 Q = aai_add2(aai_f2(g0m), icf);
+    const AaiF2 dq = aai_sub2(Q, qA);
+    const AaiF2 qr = aai_sub2(qB, Q);
+    const float ex_a = fminf(dq.x, qr.x), ex_b = fminf(dq.y, qr.y);
+    const AaiF2 along = aai_mul2(dq, aai_f2(g.ik));
+    const AaiF2 rel = aai_add2(aai_sub2(pA, aai_f2(g0M)), along);
+    const AaiF2 Mf = aai_f2(floorf(rel.x), floorf(rel.y));
+    const AaiF2 f = aai_sub2(rel, Mf), f1 = aai_sub2(aai_f2(1.0f), f);
+    const AaiF2 d_b = aai_fma2(f, aai_f2(-g.hq), aai_f2(0.5f)), d_a = aai_fma2(f1, aai_f2(-g.hq), aai_f2(0.5f));
+    const AaiF2 pc = aai_add2(aai_add2(aai_f2(g0M), Mf), aai_f2(0.5f));
+    const AaiF2 rest = aai_sub2(aai_f2(span), along);         // span - along
+    const AaiF2 af = aai_sub2(along, f), rf1 = aai_sub2(rest, f1);
+    const AaiF2 vv = aai_fma2(aai_add2(Q, aai_f2(0.5f, -0.5f)), aai_f2(g.smin), aai_mul2(pc, aai_f2(g.smax)));
+    const float vin_a = fminf(fminf(af.x, rest.x), ex_a), vout_a = fminf(g.hm - fabsf(vv.x), ex_a);
+    const float vin_b = fminf(fminf(rf1.y, along.y), ex_b), vout_b = fminf(g.hm - fabsf(vv.y), ex_b);
+    if (ex_a > -g.tau) worst = fminf(worst, fminf(f.x, f1.x));
+    if (fmaxf(vin_a, vout_a) > -g.tau) worst = fminf(worst, fminf(fabsf(vin_a), fabsf(vout_a)));
+    if (ex_b > -g.tau) worst = fminf(worst, fminf(f.y, f1.y));
+    if (fmaxf(vin_b, vout_b) > -g.tau) worst = fminf(worst, fminf(fabsf(vin_b), fabsf(vout_b)));
+    mi[0] = (int)icf.x - 1;
+    mi[1] = (int)icf.y - 1;
+    Mi[0] = (int)Mf.x;
+    Mi[1] = (int)Mf.y;
+    d_before[0] = vin_a > 0.0f ? d_b.x : 0.0f;   // ALPHA: before = corner inside (+), after = corner outside (-)
+    d_after[0] = vout_a > 0.0f ? -d_a.x : 0.0f;
+    d_before[1] = vout_b > 0.0f ? -d_b.y : 0.0f;  // BETA: the other way round
+    d_after[1] = vin_b > 0.0f ? d_a.y : 0.0f;
+}
+
 // Stand-alone FP32 form for one pair (tests): (fx, fy) = footprint centre minus the nearest integer lattice point,
 // (di, dj) = cell index relative to that lattice point.
 AAI_HD float aai_pair_area_f32(const AaiShapeF &g, float fx, float fy, int di, int dj, float &worst) {

@@ -314,13 +314,12 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                     acc[ch] = fmaf(LoadF<TI>::get(p1 + ch * (int)sizeof(TI)), d_after, acc[ch]);
                 }
             };
-            for (int q = 0; q < g.ncross; ++q) {
-                int mi, Mi;
-                float db, da;
-                aai_edge_quirk_f32<true>(g, g0m, g0M, q, mi, Mi, db, da, worst);
-                fix2(mi, Mi, db, da);
-                aai_edge_quirk_f32<false>(g, g0m, g0M, q, mi, Mi, db, da, worst);
-                fix2(mi, Mi, db, da);
+            for (int q = 0; q < g.ncross; ++q) {  // both left/right edges per packed instruction
+                int mi[2], Mi[2];
+                float db[2], da[2];
+                aai_edge_quirk_pair_f32(g, g0m, g0M, q, mi, Mi, db, da, worst);
+                fix2(mi[0], Mi[0], db[0], da[0]);
+                fix2(mi[1], Mi[1], db[1], da[1]);
             }
         }
         if (GROUPED) {  // the (at most) four source pixels, once each

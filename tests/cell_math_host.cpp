@@ -206,3 +206,23 @@ extern "C" float aai_test_footprint_edges_f32(double c, double s, double L, doub
     *total = sum;
     return worst;
 }
+
+
+// The packed two-edge routine against the scalar one: returns the number of mismatching outputs over n random grids.
+extern "C" long long aai_test_edge_pair_vs_scalar(double c, double s, double L, const double *g0m, const double *g0M,
+                                                  long long n) {
+    const AaiShapeF g = make_shape_f(c, s, L);
+    long long bad = 0;
+    for (long long k = 0; k < n; ++k)
+        for (int q = 0; q < g.ncross; ++q) {
+            int mi[2], Mi[2], m0, M0, m1, M1;
+            float db[2], da[2], b0, a0, b1, a1, w = 1.0f, w0 = 1.0f;
+            aai_edge_quirk_pair_f32(g, (float)g0m[k], (float)g0M[k], q, mi, Mi, db, da, w);
+            aai_edge_quirk_f32<true>(g, (float)g0m[k], (float)g0M[k], q, m0, M0, b0, a0, w0);
+            aai_edge_quirk_f32<false>(g, (float)g0m[k], (float)g0M[k], q, m1, M1, b1, a1, w0);
+            if (mi[0] != m0 || Mi[0] != M0 || mi[1] != m1 || Mi[1] != M1 || db[0] != b0 || da[0] != a0 || db[1] != b1 ||
+                da[1] != a1 || w != w0)
+                ++bad;
+        }
+    return bad;
+}

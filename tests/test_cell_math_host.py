@@ -25,6 +25,8 @@ def cellmath(built):
     lib.aai_test_footprint_rows_f32.restype = C.c_float
     lib.aai_test_footprint_edges_f32.argtypes = [C.c_double] * 5 + [C.c_int] * 3 + [C.c_void_p] * 2
     lib.aai_test_footprint_edges_f32.restype = C.c_float
+    lib.aai_test_edge_pair_vs_scalar.argtypes = [C.c_double] * 3 + [C.c_void_p] * 2 + [C.c_longlong]
+    lib.aai_test_edge_pair_vs_scalar.restype = C.c_longlong
     lib.aai_test_pair_areas_f32x2.argtypes = [C.c_double] * 3 + [C.c_void_p] * 7 + [C.c_longlong]
     return lib
 
@@ -239,3 +241,17 @@ def test_edge_crossings_next_to_a_lattice_corner_are_flagged(cellmath):
         total = np.zeros(1, dtype=np.float32)
         worst = cellmath.aai_test_footprint_edges_f32(c, s, side, cx, cy, i0, j0, n, got.ctypes.data, total.ctypes.data)
         assert worst < tau
+
+
+@pytest.mark.parametrize("theta,side", [(17.3, 2.7027027), (30.0, 2.7027027), (45.0, 1.7647059), (61.0, 2.0),
+                                        (5.0, 3.3), (85.0, 1.5), (73.0, 3.9), (40.0, 5.1)])
+def test_packed_two_edge_routine_equals_the_scalar_one(cellmath, theta, side):
+    """aai_edge_quirk_pair_f32 (lane x = ALPHA edge, lane y = BETA edge, what the kernel runs) must reproduce
+    aai_edge_quirk_f32 bit for bit: cells, corrections and decision margin."""
+    rng = np.random.default_rng(int(theta * 7))
+    c, s = np.cos(np.radians(theta)), np.sin(np.radians(theta))
+    n = 50000
+    hb = side / 2 * (c + s)
+    g0m = -(hb + rng.uniform(0.0, 1.0, n))   # left boundary of column 0 / top of row 0 relative to the centre
+    g0M = -(hb + rng.uniform(0.0, 1.0, n))
+    assert cellmath.aai_test_edge_pair_vs_scalar(c, s, side, g0m.ctypes.data, g0M.ctypes.data, n) == 0
