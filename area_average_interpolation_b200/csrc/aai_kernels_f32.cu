@@ -287,12 +287,14 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 Mi = max(0, min(Mi, Mlim));
                 const int k = g.steep ? mi : Mi, r = g.steep ? Mi : mi;
                 if (GROUPED) {  // corrections go to the weights of the cells' source pixels: no loads here
+                    // (group membership as 0/1 factors: four FMAs instead of four selects + four adds)
                     auto add_w = [&](int kk, int rr, float d) {
-                        const bool a = (colA >> kk) & 1u, t = (rowTop >> rr) & 1u;
-                        W00 += (t && a) ? d : 0.0f;
-                        W01 += (t && !a) ? d : 0.0f;
-                        W10 += (!t && a) ? d : 0.0f;
-                        W11 += (!t && !a) ? d : 0.0f;
+                        const float a = (float)((colA >> kk) & 1u), t = (float)((rowTop >> rr) & 1u);
+                        const float at = a * t, ab = a - at, bt = t - at;
+                        W00 = fmaf(at, d, W00);
+                        W01 = fmaf(bt, d, W01);
+                        W10 = fmaf(ab, d, W10);
+                        W11 = fmaf((1.0f - a) - bt, d, W11);
                     };
                     add_w(k, r, d_before);
                     add_w(k + (g.steep ? 1 : 0), r + (g.steep ? 0 : 1), d_after);
@@ -321,6 +323,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 fix2(mi[0], Mi[0], db[0], da[0]);
                 fix2(mi[1], Mi[1], db[1], da[1]);
             }
+
         }
         if (GROUPED) {  // the (at most) four source pixels, once each
             const int64_t roff0 = row_off(jy0), roffL = row_off(jy1), coff0 = col_off(ix0), coffL = col_off(ix1);
