@@ -126,20 +126,8 @@ AaiKernelParams aai_make_kernel_params(const aai_plan &p, const aai_image &src, 
         k.aff_yy = p.side * c;
         k.ext32 = (float)(h * (c + s) + 0.5 + 2e-6);
     }
-    AaiShape &g = k.shape;
-    g.cs = c;
-    g.sn = s;
-    g.half = h;
-    g.hc = h * c;
-    g.hs = h * s;
-    g.k_sc = s / c;
-    g.k_hc = h / c;
-    g.k_cs = c / s;  // +inf when the reduced angle is exactly 0: the separable path never reads it
-    g.k_hs = h / s;
-    g.inv_c = 1.0 / c;
-    g.inv_s = 1.0 / s;
-    g.m = (c + s) / 2;
-    g.thr = std::fabs(c - s) / 2;
+    k.shape = aai_make_shape(c, s, p.side);
+    const AaiShape &g = k.shape;
     // FP32 constants incl. the guard band of the FP32 shape decisions; near-axis angles (1/sin or 1/cos > 20) use the
     // FP64 kernel
     k.shapef = aai_make_shape_f(c, s, p.side);

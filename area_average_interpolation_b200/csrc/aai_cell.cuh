@@ -29,7 +29,42 @@ struct AaiShape {
     double inv_c, inv_s;
     double m;          // (c+s)/2: half extent of a unit cell along u or v
     double thr;        // |c-s|/2: a line isolates exactly one cell corner iff thr < |dist| < m
+    // per-edge quirk events (aai_edge_quirk_f64; same meaning as the AaiShapeF fields of the same names)
+    double hb, he, ik, hq, smin, smax, hm, area_total;
+    int steep, ncross;
 };
+
+// image-wide FP64 constants (host side; shared by the C ABI and the CPU tests)
+inline AaiShape aai_make_shape(double c, double s, double L) {
+    AaiShape g;
+    const double h = L / 2;
+    g.cs = c;
+    g.sn = s;
+    g.half = h;
+    g.hc = h * c;
+    g.hs = h * s;
+    g.k_sc = s / c;
+    g.k_hc = h / c;
+    g.k_cs = c / s;  // +inf when the reduced angle is exactly 0: the separable path never reads it
+    g.k_hs = h / s;
+    g.inv_c = 1.0 / c;
+    g.inv_s = 1.0 / s;
+    g.m = (c + s) / 2;
+    g.thr = fabs(c - s) / 2;
+    const double mn = s < c ? s : c, mx = s < c ? c : s;
+    g.hb = h * (c + s);
+    g.he = h * fabs(c - s);
+    g.ik = mx / mn;
+    g.hq = (1.0 + mn / mx) / 2;
+    g.smin = mn;
+    g.smax = mx;
+    g.hm = h - (c + s) / 2;
+    g.area_total = L * L;
+    g.steep = s <= c ? 1 : 0;
+    const double nc = floor(L * mn) + 1;
+    g.ncross = nc < 1e6 ? (int)nc : 1000000;
+    return g;
+}
 
 // chord of the footprint on the horizontal grid line y = Cy + ty:  x in Cx + [xl, xr]  (empty if xl > xr)
 AAI_HD void aai_chord_h(const AaiShape &g, double ty, double &xl, double &xr) {
@@ -512,6 +547,46 @@ AAI_HD void aai_edge_quirk_pair_f32(const AaiShapeF &g, float g0m, float g0M, in
     d_after[0] = vout_a > 0.0f ? -d_a.x : 0.0f;
     d_before[1] = vout_b > 0.0f ? -d_b.y : 0.0f;  // BETA: the other way round
     d_after[1] = vin_b > 0.0f ? d_a.y : 0.0f;
+}
+
+// FP64 form of aai_edge_quirk_f32 (the unrolled FP64 kernel): decisions are made directly on FP64 margins, there is no
+// guard band.
+template <bool ALPHA>
+AAI_HD void aai_edge_quirk_f64(const AaiShape &g, double g0m, double g0M, int n, int &mi, int &Mi, double &d_before,
+                               double &d_after) {
+    const double qA = ALPHA ? -g.hb : g.he, qB = ALPHA ? -g.he : g.hb;
+    const double pA = ALPHA ? -g.he : -g.hb;
+    const double span = g.hb + g.he;
+    const double icf = ceil(qA - g0m) + (double)n;
+    const double Q = g0m + icf;
+    const double dq = Q - qA;
+    const double ex = fmin(dq, qB - Q);
+    const double along = dq * g.ik;
+    const double rel = (pA - g0M) + along;
+    const double Mf = floor(rel);
+    const double f = rel - Mf, f1 = 1.0 - f;
+    const double d_b = 0.5 - f * g.hq, d_a = 0.5 - f1 * g.hq;
+    const double pc = (g0M + Mf) + 0.5;
+    double val_in, val_out;
+    if (ALPHA) {
+        val_in = fmin(along - f, span - along);
+        val_out = g.hm - fabs((Q + 0.5) * g.smin + pc * g.smax);
+    } else {
+        val_in = fmin((span - along) - f1, along);
+        val_out = g.hm - fabs((Q - 0.5) * g.smin + pc * g.smax);
+    }
+    val_in = fmin(val_in, ex);
+    val_out = fmin(val_out, ex);
+    // (saturating conversions: a crossing that does not exist can lie far outside the int range at tiny angles)
+    mi = icf > -1e9 && icf < 1e9 ? (int)icf - 1 : -1;
+    Mi = Mf > -1e9 && Mf < 1e9 ? (int)Mf : -1;
+    if (ALPHA) {
+        d_before = val_in > 0.0 ? d_b : 0.0;
+        d_after = val_out > 0.0 ? -d_a : 0.0;
+    } else {
+        d_before = val_out > 0.0 ? -d_b : 0.0;
+        d_after = val_in > 0.0 ? d_a : 0.0;
+    }
 }
 
 // Stand-alone FP32 form for one pair (tests): (fx, fy) = footprint centre minus the nearest integer lattice point,

@@ -56,6 +56,11 @@ int aai_launch_overlap_f32_n4(const AaiKernelParams &kp, int src_dtype, int dst_
 int aai_launch_overlap_f32_n5(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_overlap_f32_n6(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_overlap_f32_n8(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
+// aai_kernels_f64.cu, likewise (unrolled FP64 kernel; cudaErrorNotSupported -> the rolled kernel in aai_kernels.cu)
+int aai_launch_overlap_f64_n4(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
+int aai_launch_overlap_f64_n5(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
+int aai_launch_overlap_f64_n6(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
+int aai_launch_overlap_f64_n8(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
 
 void aai_set_error(const char *fmt, ...);
 

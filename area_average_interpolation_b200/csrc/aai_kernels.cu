@@ -18,6 +18,7 @@
 
 #include <cfloat>
 #include <cstdint>
+#include <cstdlib>
 
 #include "aai_device.cuh"
 
@@ -275,6 +276,16 @@ int aai_launch_overlap(const AaiKernelParams &kp, int arith, int src_dtype, int 
         if (n <= 5) return aai_launch_overlap_f32_n5(kp, src_dtype, dst_dtype, stream);
         if (n <= 6) return aai_launch_overlap_f32_n6(kp, src_dtype, dst_dtype, stream);
         if (n <= 8) return aai_launch_overlap_f32_n8(kp, src_dtype, dst_dtype, stream);
+    }
+    // FP64 arithmetic: the unrolled kernel when the footprint fits its register arrays, else the rolled one
+    if (kp.shape.sn > 0.0 && kp.shape.cs > 0.0 && !getenv("AAI_F64_ROLLED")) {
+        const int n = (int)floor(2.0 * kp.hb + 1.0 + 2e-9) + 1;  // cells per axis within hb + 1/2 + 1e-9 of the centre
+        int e = (int)cudaErrorNotSupported;
+        if (n <= 4) e = aai_launch_overlap_f64_n4(kp, src_dtype, dst_dtype, stream);
+        else if (n <= 5) e = aai_launch_overlap_f64_n5(kp, src_dtype, dst_dtype, stream);
+        else if (n <= 6) e = aai_launch_overlap_f64_n6(kp, src_dtype, dst_dtype, stream);
+        else if (n <= 8) e = aai_launch_overlap_f64_n8(kp, src_dtype, dst_dtype, stream);
+        if (e != (int)cudaErrorNotSupported) return e;
     }
     return (int)launch_any(K_OVERLAP, kp, src_dtype, dst_dtype, (cudaStream_t)stream);
 }

@@ -3,15 +3,7 @@
 #include <cmath>
 #include "../area_average_interpolation_b200/csrc/aai_cell.cuh"
 
-static AaiShape make_shape(double c, double s, double L) {
-    AaiShape g;
-    g.cs = c; g.sn = s; g.half = L / 2;
-    g.hc = g.half * c; g.hs = g.half * s;
-    g.k_sc = s / c; g.k_hc = g.half / c; g.k_cs = c / s; g.k_hs = g.half / s;
-    g.inv_c = 1.0 / c; g.inv_s = 1.0 / s;
-    g.m = (c + s) / 2; g.thr = std::fabs(c - s) / 2;
-    return g;
-}
+static AaiShape make_shape(double c, double s, double L) { return aai_make_shape(c, s, L); }
 
 extern "C" void aai_test_pair_areas(double c, double s, double L, const double *cx, const double *cy, const int *i,
                                     const int *j, double *out, long long n) {
@@ -225,4 +217,43 @@ extern "C" long long aai_test_edge_pair_vs_scalar(double c, double s, double L, 
                 ++bad;
         }
     return bad;
+}
+
+
+// FP64 edge formulation (what the unrolled FP64 kernel runs): exact Green areas + per-edge events, n x n block.
+extern "C" void aai_test_footprint_edges_f64(double c, double s, double L, double cx, double cy, int i0, int j0, int n,
+                                             double *out, double *total) {
+    const AaiShape g = make_shape(c, s, L);
+    for (int r = 0; r < n; ++r)
+        for (int k = 0; k < n; ++k) {
+            const double rx = (double)(i0 + k) - cx, ry = (double)(j0 + r) - cy;
+            double xlT, xrT, xlB, xrB, ytL, ybL, ytR, ybR;
+            aai_chord_h(g, ry - 0.5, xlT, xrT);
+            aai_chord_h(g, ry + 0.5, xlB, xrB);
+            aai_chord_v(g, rx - 0.5, ytL, ybL);
+            aai_chord_v(g, rx + 0.5, ytR, ybR);
+            out[r * n + k] = aai_cell_area(g, rx, ry, aai_overlap1(xlT, xrT, rx), aai_overlap1(xlB, xrB, rx),
+                                           aai_overlap1(ytL, ybL, ry), aai_overlap1(ytR, ybR, ry), false);
+        }
+    const double e0 = ((double)i0 - cx) - 0.5, t0 = ((double)j0 - cy) - 0.5;
+    const double g0m = g.steep ? e0 : t0, g0M = g.steep ? t0 : e0;
+    double sum = g.area_total;
+    auto apply = [&](int mi, int Mi, double d) {
+        const int k = g.steep ? mi : Mi, r = g.steep ? Mi : mi;
+        if (d != 0.0 && k >= 0 && k < n && r >= 0 && r < n) {
+            out[r * n + k] += d;
+            sum += d;
+        }
+    };
+    for (int q = 0; q < g.ncross; ++q) {
+        int mi, Mi;
+        double db, da;
+        aai_edge_quirk_f64<true>(g, g0m, g0M, q, mi, Mi, db, da);
+        apply(mi, Mi, db);
+        apply(mi + 1, Mi, da);
+        aai_edge_quirk_f64<false>(g, g0m, g0M, q, mi, Mi, db, da);
+        apply(mi, Mi, db);
+        apply(mi + 1, Mi, da);
+    }
+    *total = sum;
 }

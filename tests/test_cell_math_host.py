@@ -25,6 +25,7 @@ def cellmath(built):
     lib.aai_test_footprint_rows_f32.restype = C.c_float
     lib.aai_test_footprint_edges_f32.argtypes = [C.c_double] * 5 + [C.c_int] * 3 + [C.c_void_p] * 2
     lib.aai_test_footprint_edges_f32.restype = C.c_float
+    lib.aai_test_footprint_edges_f64.argtypes = [C.c_double] * 5 + [C.c_int] * 3 + [C.c_void_p] * 2
     lib.aai_test_edge_pair_vs_scalar.argtypes = [C.c_double] * 3 + [C.c_void_p] * 2 + [C.c_longlong]
     lib.aai_test_edge_pair_vs_scalar.restype = C.c_longlong
     lib.aai_test_pair_areas_f32x2.argtypes = [C.c_double] * 3 + [C.c_void_p] * 7 + [C.c_longlong]
@@ -255,3 +256,34 @@ def test_packed_two_edge_routine_equals_the_scalar_one(cellmath, theta, side):
     g0m = -(hb + rng.uniform(0.0, 1.0, n))   # left boundary of column 0 / top of row 0 relative to the centre
     g0M = -(hb + rng.uniform(0.0, 1.0, n))
     assert cellmath.aai_test_edge_pair_vs_scalar(c, s, side, g0m.ctypes.data, g0M.ctypes.data, n) == 0
+
+
+@pytest.mark.parametrize("theta,side", [(17.3, 2.7027027), (30.0, 2.7027027), (45.0, 1.7647059), (61.0, 2.0),
+                                        (1.5, 5.905), (89.2, 1.5), (73.0, 3.9), (0.05, 2.0), (44.999, 2.0)])
+def test_fp64_edge_formulation_matches_the_per_cell_form(cellmath, theta, side):
+    """The unrolled FP64 kernel's formulation (exact areas + per-edge crossing events in FP64, no guard band) against
+    the per-cell FP64 form that is checked against the oracle above -- also for angles next to the axes, which only
+    the FP64 kernels serve."""
+    rng = np.random.default_rng(int(theta * 100) + 9)
+    c, s = np.cos(np.radians(theta)), np.sin(np.radians(theta))
+    n = int(np.floor(side * (c + s) + 1)) + 2
+    bad = 0
+    trials = 3000
+    for _ in range(trials):
+        cx, cy = rng.uniform(100, 116, 2)
+        i0 = int(np.ceil(cx - (side / 2 * (c + s) + 0.5)))
+        j0 = int(np.ceil(cy - (side / 2 * (c + s) + 0.5)))
+        got = np.zeros(n * n)
+        total = np.zeros(1)
+        cellmath.aai_test_footprint_edges_f64(c, s, side, cx, cy, i0, j0, n, got.ctypes.data, total.ctypes.data)
+        ii, jj = np.meshgrid(np.arange(i0, i0 + n), np.arange(j0, j0 + n))
+        i = ii.ravel().astype(np.int32)
+        j = jj.ravel().astype(np.int32)
+        want = np.zeros(n * n)
+        cxa, cya = np.full(n * n, cx), np.full(n * n, cy)
+        cellmath.aai_test_pair_areas(c, s, side, cxa.ctypes.data, cya.ctypes.data, i.ctypes.data, j.ctypes.data,
+                                     want.ctypes.data, n * n)
+        amp = max(1.0, 1.0 / c, 1.0 / s)
+        if np.abs(got - want).max() > 1e-12 * amp or abs(total[0] - want.sum()) > 1e-11 * amp:
+            bad += 1
+    assert bad == 0
