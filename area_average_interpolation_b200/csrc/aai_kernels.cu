@@ -278,7 +278,10 @@ int aai_launch_overlap(const AaiKernelParams &kp, int arith, int src_dtype, int 
         if (n <= 8) return aai_launch_overlap_f32_n8(kp, src_dtype, dst_dtype, stream);
     }
     // FP64 arithmetic: the unrolled kernel when the footprint fits its register arrays, else the rolled one
-    if (kp.shape.sn > 0.0 && kp.shape.cs > 0.0 && !getenv("AAI_F64_ROLLED")) {
+    // (its general-frame addressing divides by the scale with a multiply-high, exact below 2^32 / scale)
+    const uint64_t max_e = (uint64_t)(kp.mod_w > kp.mod_h ? kp.mod_w : kp.mod_h);
+    if (kp.shape.sn > 0.0 && kp.shape.cs > 0.0 && max_e * (uint64_t)kp.scale < 0x100000000ULL &&
+        !getenv("AAI_F64_ROLLED")) {
         const int n = (int)floor(2.0 * kp.hb + 1.0 + 2e-9) + 1;  // cells per axis within hb + 1/2 + 1e-9 of the centre
         int e = (int)cudaErrorNotSupported;
         if (n <= 4) e = aai_launch_overlap_f64_n4(kp, src_dtype, dst_dtype, stream);

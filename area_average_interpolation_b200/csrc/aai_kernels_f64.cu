@@ -58,13 +58,32 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 512 / (TILE_W *TILE_H))
         for (int k = 0; k < MAXN; ++k) lenTop[k] = aai_overlap1(xlT, xrT, rx0 + (double)k);
         constexpr int ESZ = (int)sizeof(TI) * NC;
         const char *rowp0 = (const char *)kp.src + (int64_t)(jy0 - kp.src_y0) * kp.src_pitch + (int64_t)ix0 * ESZ;
-        auto cell_ptr = [&](int k, int r) -> const char * {  // source element of cell (column k, row r)
+        // General frame: expanded pixel (i,j) -> source pixel is separable (one source coordinate depends on the column
+        // only, the other on the row only; swapped for quadrants 1/3): byte offset = col_off(i) + row_off(j), the column
+        // parts hoisted out of the row loop (as in the FP32 kernel).
+        const bool swapped = kp.e_axi == 0;
+        auto div_s = [&](int e) -> int64_t {
+            return (int64_t)(kp.scale != 1 ? __umulhi((unsigned)e, kp.div_magic) : (unsigned)e);
+        };
+        auto col_off = [&](int i) -> int64_t {
+            return swapped ? (div_s(kp.e_ayi * i + kp.e_ay0) - kp.src_y0) * kp.src_pitch
+                           : div_s(kp.e_axi * i + kp.e_ax0) * ESZ;
+        };
+        auto row_off = [&](int j) -> int64_t {
+            return swapped ? div_s(kp.e_axj * j + kp.e_ax0) * ESZ
+                           : (div_s(kp.e_ayj * j + kp.e_ay0) - kp.src_y0) * kp.src_pitch;
+        };
+        int64_t coff[MAXN];
+        if (!IDENT) {
+#pragma unroll
+            for (int k = 0; k < MAXN; ++k) coff[k] = col_off(ix0 + min(k, ncols - 1));
+        }
+        auto cell_ptr = [&](int k, int r) -> const char * {  // source element of cell (column k, row r), any k
             if (IDENT) return rowp0 + (int64_t)r * kp.src_pitch + (int64_t)k * ESZ;
-            int sx, sy;
-            mod_to_src(kp, ix0 + k, jy0 + r, sx, sy);
-            return (const char *)kp.src + (int64_t)(sy - kp.src_y0) * kp.src_pitch + (int64_t)sx * ESZ;
+            return (const char *)kp.src + row_off(jy0 + r) + col_off(ix0 + k);
         };
         for (int r = 0; r < nrows; ++r) {
+            const char *rowp = IDENT ? rowp0 + (int64_t)r * kp.src_pitch : (const char *)kp.src + row_off(jy0 + r);
             const double ry = ry0 + (double)r;
             double xlB, xrB;
             aai_chord_h(g, ry + 0.5, xlB, xrB);
@@ -78,7 +97,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 512 / (TILE_W *TILE_H))
                 lenTop[k] = lenB;
                 lenL = lenR;
                 if (k < ncols) {  // columns beyond the footprint box are never read (their area is exactly 0)
-                    const char *p = cell_ptr(k, r);
+                    const char *p = IDENT ? rowp + k * ESZ : rowp + coff[k];
 #pragma unroll
                     for (int ch = 0; ch < NC; ++ch) acc[ch] = fma(SrcLoad<TI>::get(p, ch), area, acc[ch]);
                 }
