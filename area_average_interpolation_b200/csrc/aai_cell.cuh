@@ -123,6 +123,23 @@ AAI_HD double aai_cell_area(const AaiShape &g, double rx, double ry, double lenT
     return area;
 }
 
+// Exact overlap only (no quirk), Green form with the vertex rotation folded into the side coefficients (the form the
+// FP32 kernel uses, in FP64): what the unrolled FP64 kernel evaluates per cell.
+AAI_HD double aai_cell_exact_f64(const AaiShape &g, double rx, double ry, double lenT, double lenB, double lenL,
+                                 double lenR) {
+    const double u0 = rx * g.cs - ry * g.sn;
+    const double v0 = rx * g.sn + ry * g.cs;
+    const double ca = copysign(g.half, u0) - u0;  // V - cell centre along u, v
+    const double cb = copysign(g.half, v0) - v0;
+    const double aT = 0.25 + 0.5 * (cb * g.cs - ca * g.sn);
+    const double aL = 0.25 + 0.5 * (ca * g.cs + cb * g.sn);
+    return aT * (lenT - lenB) + (aL * (lenL - lenR) + 0.5 * (lenB + lenR));
+}
+// value of x clamped into the chord [lo, hi] (hi < lo, a grid line that misses the footprint, gives hi for every x):
+// the length of [lo,hi] inside [a,b] is clamp(b) - clamp(a), bit-identical to aai_overlap1 and one min/max cheaper when
+// consecutive cells share a boundary
+AAI_HD double aai_clamp_chord(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+
 // Stand-alone form for one (footprint centre, cell) pair: computes the four chords itself.
 AAI_HD double aai_pair_area(const AaiShape &g, double cx, double cy, int i, int j) {
     const double rx = (double)i - cx, ry = (double)j - cy;

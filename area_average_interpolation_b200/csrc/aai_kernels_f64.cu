@@ -54,8 +54,18 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 512 / (TILE_W *TILE_H))
         double xlT, xrT;
         aai_chord_h(g, t0, xlT, xrT);
         double lenTop[MAXN];  // the cells' top sides inside the footprint: the previous row's bottom sides
+        {
+            double prev = aai_clamp_chord(e0, xlT, xrT);
 #pragma unroll
-        for (int k = 0; k < MAXN; ++k) lenTop[k] = aai_overlap1(xlT, xrT, rx0 + (double)k);
+            for (int k = 0; k < MAXN; ++k) {
+                const double next = aai_clamp_chord(e0 + (double)(k + 1), xlT, xrT);
+                lenTop[k] = next - prev;
+                prev = next;
+            }
+        }
+        double cv[MAXN + 1];  // vertical chords clamped at the top of the current row
+#pragma unroll
+        for (int k = 0; k <= MAXN; ++k) cv[k] = aai_clamp_chord(t0, yt[k], yb[k]);
         constexpr int ESZ = (int)sizeof(TI) * NC;
         const char *rowp0 = (const char *)kp.src + (int64_t)(jy0 - kp.src_y0) * kp.src_pitch + (int64_t)ix0 * ESZ;
         // General frame: expanded pixel (i,j) -> source pixel is separable (one source coordinate depends on the column
@@ -87,13 +97,21 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 512 / (TILE_W *TILE_H))
             const double ry = ry0 + (double)r;
             double xlB, xrB;
             aai_chord_h(g, ry + 0.5, xlB, xrB);
-            double lenL = aai_overlap1(yt[0], yb[0], ry);
+            const double yb1 = ry + 0.5;  // bottom of this row
+            double cnext = aai_clamp_chord(yb1, yt[0], yb[0]);
+            double lenL = cnext - cv[0];
+            cv[0] = cnext;
+            double hprev = aai_clamp_chord(e0, xlB, xrB);
 #pragma unroll
             for (int k = 0; k < MAXN; ++k) {
                 const double rx = rx0 + (double)k;
-                const double lenR = aai_overlap1(yt[k + 1], yb[k + 1], ry);
-                const double lenB = aai_overlap1(xlB, xrB, rx);
-                const double area = aai_cell_area(g, rx, ry, lenTop[k], lenB, lenL, lenR, false);
+                cnext = aai_clamp_chord(yb1, yt[k + 1], yb[k + 1]);
+                const double lenR = cnext - cv[k + 1];
+                cv[k + 1] = cnext;
+                const double hnext = aai_clamp_chord(e0 + (double)(k + 1), xlB, xrB);
+                const double lenB = hnext - hprev;
+                hprev = hnext;
+                const double area = aai_cell_exact_f64(g, rx, ry, lenTop[k], lenB, lenL, lenR);
                 lenTop[k] = lenB;
                 lenL = lenR;
                 if (k < ncols) {  // columns beyond the footprint box are never read (their area is exactly 0)

@@ -232,8 +232,12 @@ extern "C" void aai_test_footprint_edges_f64(double c, double s, double L, doubl
             aai_chord_h(g, ry + 0.5, xlB, xrB);
             aai_chord_v(g, rx - 0.5, ytL, ybL);
             aai_chord_v(g, rx + 0.5, ytR, ybR);
-            out[r * n + k] = aai_cell_area(g, rx, ry, aai_overlap1(xlT, xrT, rx), aai_overlap1(xlB, xrB, rx),
-                                           aai_overlap1(ytL, ybL, ry), aai_overlap1(ytR, ybR, ry), false);
+            // the kernel's arithmetic: side lengths as differences of clamped boundaries, folded Green form
+            const double a = rx - 0.5, b = rx + 0.5, t = ry - 0.5, u = ry + 0.5;
+            out[r * n + k] = aai_cell_exact_f64(g, rx, ry, aai_clamp_chord(b, xlT, xrT) - aai_clamp_chord(a, xlT, xrT),
+                                                aai_clamp_chord(b, xlB, xrB) - aai_clamp_chord(a, xlB, xrB),
+                                                aai_clamp_chord(u, ytL, ybL) - aai_clamp_chord(t, ytL, ybL),
+                                                aai_clamp_chord(u, ytR, ybR) - aai_clamp_chord(t, ytR, ybR));
         }
     const double e0 = ((double)i0 - cx) - 0.5, t0 = ((double)j0 - cy) - 0.5;
     const double g0m = g.steep ? e0 : t0, g0M = g.steep ? t0 : e0;
