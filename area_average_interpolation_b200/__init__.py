@@ -104,6 +104,8 @@ def lib() -> C.CDLL:
         L.aai_ipc_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
         L.aai_ipc_close.restype = C.c_int
         L.aai_ipc_close.argtypes = [C.c_void_p, C.c_int]
+        L.aai_measure_fp32_tflops.restype = C.c_int
+        L.aai_measure_fp32_tflops.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.aai_expand_device.restype = C.c_int
         L.aai_expand_device.argtypes = [C.POINTER(Plan), C.POINTER(Image), C.POINTER(Image), C.c_int, C.c_void_p]
         L.aai_run_device.restype = C.c_int
@@ -264,6 +266,13 @@ def ipc_close(device_ptr: int, device: int) -> None:
     _check(lib().aai_ipc_close(C.c_void_p(device_ptr), int(device)))
 
 
+def measure_fp32_tflops(device: int = 0) -> float:
+    """``aai_measure_fp32_tflops``: sustained FP32 FMA rate of the device (roofline denominator of bench.py)."""
+    v = C.c_double(0.0)
+    _check(lib().aai_measure_fp32_tflops(int(device), C.byref(v)))
+    return v.value
+
+
 def expand_device(plan: Plan, src_img: Image, dst_mod_img: Image, device: int = 0, stream: int = 0) -> None:
     """``aai_expand_device``: the reference's expanded + quadrant-rotated source ``modSrc`` (Source.cpp:157-172)."""
     _check(lib().aai_expand_device(C.byref(plan), C.byref(src_img), C.byref(dst_mod_img), int(device), C.c_void_p(stream)))
@@ -368,7 +377,7 @@ class AreaAverageInterpolation:
 
 __all__ = [
     "AreaAverageInterpolation", "Result", "Plan", "Image", "AaiError", "make_plan", "partition_rows",
-    "band_source_window", "covered_pixels", "device_count", "launch_count", "last_host_timing", "run_device", "run_device_batch", "expand_device", "image_alloc", "image_free", "image_upload", "image_download", "image_copy_rows",
+    "band_source_window", "covered_pixels", "device_count", "launch_count", "last_host_timing", "run_device", "run_device_batch", "expand_device", "measure_fp32_tflops", "image_alloc", "image_free", "image_upload", "image_download", "image_copy_rows",
     "ipc_export", "ipc_open", "ipc_close",
     "run_host", "run_host_band", "tensor_image", "status_string", "last_error", "lib", "LIB_PATH",
 ]

@@ -390,6 +390,40 @@ int aai_expand_device(const aai_plan *plan, const aai_image *src, const aai_imag
     return AAI_OK;
 }
 
+int aai_measure_fp32_tflops(int device, double *tflops) {
+    if (!tflops) {
+        aai_set_error("aai_measure_fp32_tflops: null result");
+        return AAI_ERR_ARGUMENT;
+    }
+    AAI_CUDA(cudaSetDevice(device));
+    int sms = 0;
+    AAI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    float *scratch = nullptr;
+    AAI_CUDA(cudaMalloc(&scratch, 256));
+    cudaEvent_t e0, e1;
+    AAI_CUDA(cudaEventCreate(&e0));
+    AAI_CUDA(cudaEventCreate(&e1));
+    double flop = 0.0, best = 0.0;
+    int rc = AAI_OK;
+    for (int rep = 0; rep < 4 && rc == AAI_OK; ++rep) {  // first repetition warms up
+        cudaEventRecord(e0, 0);
+        const int e = aai_probe_fp32(sms * 8, 1 << 16, scratch, &flop, nullptr);
+        cudaEventRecord(e1, 0);
+        if (e != (int)cudaSuccess || cudaEventSynchronize(e1) != cudaSuccess) {
+            rc = cuda_fail((cudaError_t)(e != (int)cudaSuccess ? e : (int)cudaGetLastError()), "FP32 probe");
+            break;
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms > 0.f && flop / (ms * 1e-3) / 1e12 > best) best = flop / (ms * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(scratch);
+    *tflops = best;
+    return rc;
+}
+
 int aai_run_device_batch(const aai_plan *plan, int mode, int arith, const aai_image *srcs, const aai_image *dsts,
                          int n_images, int device, void *stream) {
     if (!plan || !srcs || !dsts || n_images <= 0) {

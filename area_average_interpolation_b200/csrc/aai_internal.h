@@ -49,6 +49,8 @@ int aai_launch_overlap(const AaiKernelParams &kp, int arith, int src_dtype, int 
 int aai_launch_separable(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_fast(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_expand(const AaiKernelParams &kp, int elem_bytes, void *stream);
+// measurement helper: launches the FP32 FMA probe, returns the flop it performs
+int aai_probe_fp32(int blocks, int iters, float *scratch, double *flop, void *stream);
 // aai_kernels_sep.cu: TMA-staged separable kernel; returns cudaErrorNotSupported when its fast path does not apply
 int aai_launch_separable_tma(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);
 // aai_kernels_f32.cu, one translation unit per maximum cell count per axis

@@ -219,6 +219,24 @@ __global__ void __launch_bounds__(256) expand_kernel(const __grid_constant__ Aai
     for (int ch = 0; ch < kp.channels; ++ch) drow[mx * kp.channels + ch] = srow[sx * kp.channels + ch];
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Measurement helper (bench.py roofline denominator): sustained FP32 FMA rate of the device, 16 independent FFMA
+// chains per thread, 2 flop per FFMA.  Not part of the resampling path.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, float a, float b) {
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = (float)(threadIdx.x + k);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = fmaf(v[k], a, b);
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sum += v[k];
+    if (sum == 123.456f) out[0] = sum;  // never true: keeps the chains alive
+}
+
 enum KernelKind { K_OVERLAP, K_SEPARABLE, K_FAST, K_FAST_F32 };
 
 template <typename TI, typename TO, int NC>
@@ -291,6 +309,11 @@ int aai_launch_overlap(const AaiKernelParams &kp, int arith, int src_dtype, int 
         if (e != (int)cudaErrorNotSupported) return e;
     }
     return (int)launch_any(K_OVERLAP, kp, src_dtype, dst_dtype, (cudaStream_t)stream);
+}
+int aai_probe_fp32(int blocks, int iters, float *scratch, double *flop, void *stream) {
+    fp32_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(scratch, iters, 0.999f, 0.001f);
+    *flop = (double)blocks * 256.0 * 16.0 * 2.0 * (double)iters;
+    return (int)cudaGetLastError();
 }
 int aai_launch_separable(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream) {
     // TMA-staged two-pass kernel when its preconditions hold, else direct taps

@@ -461,12 +461,22 @@ def our_arm(args, cfg):
                     "algorithmic": "each source byte read once + each canvas byte written once (SURVEY 8d)"}
     else:
         F = flops_per_covered_pixel(plan.side, plan.cos_t, plan.sin_t, CH)
-        fp32_peak = n_sm * 128 * 2 * sm_max * 1e6 / 1e12
+        nominal = n_sm * 128 * 2 * sm_max * 1e6 / 1e12
+        try:  # measured on this device right now (register-only FFMA probe in the library)
+            measured = aai.measure_fp32_tflops(local)
+        except Exception as exc:
+            print(f"[bench] FP32 probe failed: {exc}", file=sys.stderr)
+            measured = 0.0
+        fp32_peak = measured if 0.5 * nominal < measured < 1.1 * nominal else nominal
         achieved = F * covered / world / (kernel_ms * 1e-3) / 1e12
         roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                     "frac": achieved / fp32_peak, "traffic": None,
-                    "peak_source": f"{n_sm} SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (no measured FP32 figure in "
-                                   "MEASURED_PEAKS.json; nominal at max clock)",
+                    "peak_source": (f"measured on this device by the library's FFMA probe ({measured:.2f} TFLOP/s; nominal "
+                                    f"{n_sm} SMs x 128 lanes x 2 x {sm_max:.0f} MHz = {nominal:.2f}; MEASURED_PEAKS.json "
+                                    "holds no FP32 figure)" if fp32_peak == measured else
+                                    f"nominal {n_sm} SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (FFMA probe unavailable; "
+                                    "MEASURED_PEAKS.json holds no FP32 figure)"),
+                    "peak_nominal": nominal,
                     "algorithmic": f"{F:.0f} flop per covered canvas pixel x {covered / world:.0f} covered pixels per "
                                    "launch (SURVEY 8d contract figure)",
                     "hbm": {"achieved": alg_bytes / world / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

@@ -160,6 +160,12 @@ int aai_ipc_close(void *device_ptr, int device);
  * materialise it; they index the source through the same map.) */
 int aai_expand_device(const aai_plan *plan, const aai_image *src, const aai_image *dst_mod, int device, void *stream);
 
+/* Measurement helper (bench.py): sustained FP32 FMA rate of `device` in TFLOP/s, measured with a register-only FFMA
+ * kernel (16 independent chains per thread).  The rotated-clip kernels are FP32-pipe bound by contract and
+ * MEASURED_PEAKS.json holds no FP32 figure, so the roofline denominator is measured here.  Nothing in the reference
+ * corresponds to it. */
+int aai_measure_fp32_tflops(int device, double *tflops);
+
 /* ---- the hot path --------------------------------------------------------------------------------------- */
 
 /* Main loop of the reference (Source.cpp:411-579 / 866-907) for canvas rows [row0,row1) on one device.
