@@ -56,6 +56,8 @@ struct Workspace {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> chunk_ev;        // 2 per chunk: upload done, kernel done
     cudaEvent_t fork = nullptr, join_up = nullptr, join_dn = nullptr;
+    cudaEvent_t done = nullptr;  // end of the last band run that used this workspace (asynchronous callers may
+    bool done_valid = false;     // use different streams: the next run waits for it before touching the buffers)
     std::mutex busy;  // held for the duration of one band run on this device
 };
 constexpr int kMaxDevices = 64;
@@ -78,6 +80,7 @@ int workspace_get(int device, size_t bytes0, size_t bytes1, Workspace **out) {
         AAI_CUDA(cudaEventCreateWithFlags(&w.fork, cudaEventDisableTiming));
         AAI_CUDA(cudaEventCreateWithFlags(&w.join_up, cudaEventDisableTiming));
         AAI_CUDA(cudaEventCreateWithFlags(&w.join_dn, cudaEventDisableTiming));
+        AAI_CUDA(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
     }
     const size_t need[2] = {bytes0, bytes1};
     for (int k = 0; k < 2; ++k) {
@@ -338,8 +341,8 @@ int aai_run_device(const aai_plan *plan, int mode, int arith, const aai_image *s
         e = aai_launch_separable(kp, arith, src->dtype, dst->dtype, stream);
     else
         e = aai_launch_overlap(kp, arith, src->dtype, dst->dtype, stream);
-    g_launches.fetch_add(1);
     if (e != (int)cudaSuccess) return cuda_fail((cudaError_t)e, "kernel launch");
+    g_launches.fetch_add(1);
     return AAI_OK;
 }
 
@@ -385,8 +388,8 @@ int aai_expand_device(const aai_plan *plan, const aai_image *src, const aai_imag
     kp.dst = dst_mod->data;
     kp.dst_pitch = dst_mod->pitch_bytes;
     const int e = aai_launch_expand(kp, (int)elem_size(src->dtype), stream);
-    g_launches.fetch_add(1);
     if (e != (int)cudaSuccess) return cuda_fail((cudaError_t)e, "expand kernel launch");
+    g_launches.fetch_add(1);
     return AAI_OK;
 }
 
@@ -399,12 +402,13 @@ int aai_measure_fp32_tflops(int device, double *tflops) {
     int sms = 0;
     AAI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     float *scratch = nullptr;
-    AAI_CUDA(cudaMalloc(&scratch, 256));
-    cudaEvent_t e0, e1;
-    AAI_CUDA(cudaEventCreate(&e0));
-    AAI_CUDA(cudaEventCreate(&e1));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     double flop = 0.0, best = 0.0;
     int rc = AAI_OK;
+    cudaError_t ce = cudaMalloc(&scratch, 256);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e0);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e1);
+    if (ce != cudaSuccess) rc = cuda_fail(ce, "FP32 probe set-up");
     for (int rep = 0; rep < 4 && rc == AAI_OK; ++rep) {  // first repetition warms up
         cudaEventRecord(e0, 0);
         const int e = aai_probe_fp32(sms * 8, 1 << 16, scratch, &flop, nullptr);
@@ -417,9 +421,9 @@ int aai_measure_fp32_tflops(int device, double *tflops) {
         cudaEventElapsedTime(&ms, e0, e1);
         if (rep > 0 && ms > 0.f && flop / (ms * 1e-3) / 1e12 > best) best = flop / (ms * 1e-3) / 1e12;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(scratch);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (scratch) cudaFree(scratch);
     *tflops = best;
     return rc;
 }
@@ -497,6 +501,9 @@ int aai_run_host_band(const aai_plan *plan, int mode, int arith, const aai_image
     dsrc.data = w->ptr[0];
     ddst.data = w->ptr[1];
     cudaStream_t st = stream ? (cudaStream_t)stream : w->stream;
+    // the workspace is shared by every run on this device: order this run after the previous one even when an
+    // asynchronous caller switched streams in between
+    if (w->done_valid) AAI_CUDA(cudaStreamWaitEvent(st, w->done, 0));
     // Pipelined path for large bands: the canvas band is cut into chunks of rows; the source halo is uploaded
     // progressively (each source row once), chunk c's kernel starts as soon as its own halo has arrived and its rows
     // are downloaded while later chunks are still uploading / computing (PCIe is full duplex).  Three streams,
@@ -521,6 +528,8 @@ int aai_run_host_band(const aai_plan *plan, int mode, int arith, const aai_image
         r = aai_image_download(dst, &ddst, device, st);
         if (r != AAI_OK) return r;
         AAI_CUDA(cudaEventRecord(w->ev[3], st));
+        AAI_CUDA(cudaEventRecord(w->done, st));
+        w->done_valid = true;
         if (synchronize || !stream) {
             AAI_CUDA(cudaStreamSynchronize(st));
             AAI_CUDA(cudaEventElapsedTime(&g_h2d_ms, w->ev[0], w->ev[1]));
@@ -591,6 +600,8 @@ int aai_run_host_band(const aai_plan *plan, int mode, int arith, const aai_image
     AAI_CUDA(cudaStreamWaitEvent(st, w->join_up, 0));
     AAI_CUDA(cudaStreamWaitEvent(st, w->join_dn, 0));
     AAI_CUDA(cudaEventRecord(w->ev[3], st));
+    AAI_CUDA(cudaEventRecord(w->done, st));
+    w->done_valid = true;
     if (synchronize || !stream) {
         AAI_CUDA(cudaStreamSynchronize(st));
         // overlapped phases cannot be separated: report the whole call as one figure
