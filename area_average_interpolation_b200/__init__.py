@@ -288,7 +288,7 @@ def run_device(plan: Plan, src_img: Image, dst_img: Image, row0: int = 0, row1: 
 
 def run_device_batch(plan: Plan, src_imgs: Sequence[Image], dst_imgs: Sequence[Image], mode: int = MODE_AREA_AVERAGE,
                      arith: int = ARITH_F64, device: int = 0, stream: int = 0) -> None:
-    """``aai_run_device_batch``: a batch of images sharing one plan (one launch when equally strided + axis-aligned)."""
+    """``aai_run_device_batch``: a batch of images sharing one plan (one launch when the images are whole and equally strided)."""
     n = len(src_imgs)
     sa, da = (Image * n)(*src_imgs), (Image * n)(*dst_imgs)
     _check(lib().aai_run_device_batch(C.byref(plan), int(mode), int(arith), sa, da, n, int(device), C.c_void_p(stream)))

@@ -435,34 +435,45 @@ int aai_run_device_batch(const aai_plan *plan, int mode, int arith, const aai_im
         return AAI_ERR_ARGUMENT;
     }
     if (plan->status != AAI_OK) return plan->status;
-    // one launch when the images form an equally strided stack of whole images and the separable TMA path applies
-    bool uniform = n_images > 1 && plan->axis_aligned && mode == AAI_MODE_AREA_AVERAGE && image_ok(&srcs[0]) &&
-                   image_ok(&dsts[0]) && srcs[0].y0 == 0 && srcs[0].rows == srcs[0].height && dsts[0].y0 == 0 &&
-                   dsts[0].rows == dsts[0].height && srcs[0].width == plan->src_w && srcs[0].height == plan->src_h &&
-                   dsts[0].width == plan->dst_w && dsts[0].height == plan->dst_h && srcs[0].channels == 1 &&
-                   dsts[0].channels == 1;
-    const int64_t sstride = uniform ? (const char *)srcs[1].data - (const char *)srcs[0].data : 0;
-    const int64_t dstride = uniform ? (const char *)dsts[1].data - (const char *)dsts[0].data : 0;
-    for (int k = 1; uniform && k < n_images; ++k) {
+    // One launch for the whole batch when the images form an equally strided stack of whole images: the separable TMA
+    // kernel takes the stack as a rank-3 tensor (grid.y = image), every other kernel as grid.z = image.
+    const aai_image &s0 = srcs[0], &d0 = dsts[0];
+    bool stack = n_images > 1 && image_ok(&s0) && image_ok(&d0) && s0.y0 == 0 && s0.rows == s0.height && d0.y0 == 0 &&
+                 d0.rows == d0.height && s0.width == plan->src_w && s0.height == plan->src_h &&
+                 d0.width == plan->dst_w && d0.height == plan->dst_h && s0.channels == d0.channels &&
+                 (mode == AAI_MODE_AREA_AVERAGE || mode == AAI_MODE_FAST || mode == AAI_MODE_AREA_AVERAGE_EXACT) &&
+                 (arith == AAI_ARITH_F64 || arith == AAI_ARITH_F32);
+    const int64_t sstride = stack ? (const char *)srcs[1].data - (const char *)s0.data : 0;
+    const int64_t dstride = stack ? (const char *)dsts[1].data - (const char *)d0.data : 0;
+    for (int k = 1; stack && k < n_images; ++k) {
         const aai_image &a = srcs[k], &b = dsts[k];
-        uniform = a.data == (const char *)srcs[0].data + k * sstride && b.data == (char *)dsts[0].data + k * dstride &&
-                  a.pitch_bytes == srcs[0].pitch_bytes && b.pitch_bytes == dsts[0].pitch_bytes &&
-                  a.dtype == srcs[0].dtype && b.dtype == dsts[0].dtype && a.width == srcs[0].width &&
-                  a.height == srcs[0].height && a.y0 == 0 && a.rows == a.height && b.width == dsts[0].width &&
-                  b.height == dsts[0].height && b.y0 == 0 && b.rows == b.height && a.channels == 1 && b.channels == 1;
+        stack = a.data == (const char *)s0.data + k * sstride && b.data == (char *)d0.data + k * dstride &&
+                a.pitch_bytes == s0.pitch_bytes && b.pitch_bytes == d0.pitch_bytes && a.dtype == s0.dtype &&
+                b.dtype == d0.dtype && a.width == s0.width && a.height == s0.height && a.y0 == 0 &&
+                a.rows == a.height && b.width == d0.width && b.height == d0.height && b.y0 == 0 &&
+                b.rows == b.height && a.channels == s0.channels && b.channels == d0.channels;
     }
-    if (uniform && sstride > 0 && dstride > 0) {
+    if (stack && sstride > 0 && dstride > 0) {
         AAI_CUDA(cudaSetDevice(device));
-        AaiKernelParams kp = aai_make_kernel_params(*plan, srcs[0], dsts[0], 0, plan->dst_h);
-        kp.batch = n_images;
-        kp.src_batch_stride = sstride;
-        kp.dst_batch_stride = dstride;
-        const int e = aai_launch_separable_tma(kp, arith, srcs[0].dtype, dsts[0].dtype, stream);
-        if (e == (int)cudaSuccess) {
+        constexpr int kMaxGridZ = 65535;
+        for (int first = 0; first < n_images; first += kMaxGridZ) {
+            const int n = n_images - first < kMaxGridZ ? n_images - first : kMaxGridZ;
+            AaiKernelParams kp = aai_make_kernel_params(*plan, srcs[first], dsts[first], 0, plan->dst_h);
+            kp.quirk = mode == AAI_MODE_AREA_AVERAGE_EXACT ? 0 : 1;
+            kp.batch = n;
+            kp.src_batch_stride = sstride;
+            kp.dst_batch_stride = dstride;
+            int e;
+            if (mode == AAI_MODE_FAST)
+                e = aai_launch_fast(kp, arith, s0.dtype, d0.dtype, stream);
+            else if (plan->axis_aligned)
+                e = aai_launch_separable(kp, arith, s0.dtype, d0.dtype, stream);
+            else
+                e = aai_launch_overlap(kp, arith, s0.dtype, d0.dtype, stream);
+            if (e != (int)cudaSuccess) return cuda_fail((cudaError_t)e, "batched kernel launch");
             g_launches.fetch_add(1);
-            return AAI_OK;
         }
-        if (e != (int)cudaErrorNotSupported) return cuda_fail((cudaError_t)e, "batched separable kernel launch");
+        return AAI_OK;
     }
     for (int k = 0; k < n_images; ++k) {
         const int r = aai_run_device(plan, mode, arith, &srcs[k], &dsts[k], 0, plan->dst_h, device, stream);

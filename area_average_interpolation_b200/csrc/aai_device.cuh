@@ -60,6 +60,15 @@ __device__ __forceinline__ void store_dst<uint8_t>(void *row, int idx, double v)
     ((uint8_t *)row)[idx] = (uint8_t)(int)r;
 }
 
+// Batched launches: gridDim.z = the images of an equally strided stack that share one plan (aai_run_device_batch);
+// blockIdx.z selects this CTA's image.  Single-image launches have gridDim.z = 1 and stride 0.
+__device__ __forceinline__ const char *src_base(const AaiKernelParams &kp) {
+    return (const char *)kp.src + (int64_t)blockIdx.z * kp.src_batch_stride;
+}
+__device__ __forceinline__ char *dst_base(const AaiKernelParams &kp) {
+    return (char *)kp.dst + (int64_t)blockIdx.z * kp.dst_batch_stride;
+}
+
 // expanded + quadrant-rotated pixel (mx,my) -> original source pixel (inverse of Source.cpp:163-168)
 __device__ __forceinline__ void mod_to_src(const AaiKernelParams &kp, int mx, int my, int &sx, int &sy) {
     int ex, ey;
@@ -129,7 +138,7 @@ __device__ __forceinline__ void pixel_f64(const AaiKernelParams &kp, double cx, 
             if (area != 0.0) {
                 int sx, sy;
                 mod_to_src(kp, i, j, sx, sy);
-                const char *row = (const char *)kp.src + (int64_t)(sy - kp.src_y0) * kp.src_pitch;
+                const char *row = src_base(kp) + (int64_t)(sy - kp.src_y0) * kp.src_pitch;
                 sumA += area;
 #pragma unroll
                 for (int ch = 0; ch < NC; ++ch) acc[ch] += SrcLoad<TI>::get(row, sx * NC + ch) * area;

@@ -36,7 +36,8 @@ struct AaiKernelParams {
     void *dst;
     int64_t dst_pitch;
     int32_t dst_y0, row0, row1;
-    // batch of equally strided images sharing one plan (separable TMA path only; 0/1 = single image)
+    // batch of equally strided images sharing one plan (0/1 = single image): blockIdx.y of the separable TMA kernel,
+    // blockIdx.z of every other kernel selects the image
     int32_t batch;
     int64_t src_batch_stride, dst_batch_stride;
 };

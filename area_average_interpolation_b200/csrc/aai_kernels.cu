@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H)
     cell_range(kp, cx, cy, ix0, ix1, jy0, jy1);
     double sumA, acc[NC];
     pixel_f64<TI, NC>(kp, cx, cy, ix0, ix1, jy0, jy1, sumA, acc);
-    char *drow = (char *)kp.dst + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
+    char *drow = dst_base(kp) + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
     const bool ok = DBL_EPSILON < fabs(sumA);  // Source.cpp:577
 #pragma unroll
     for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, ok ? acc[ch] / sumA : 0.0);
@@ -76,14 +76,14 @@ __global__ void __launch_bounds__(TILE_W *TILE_H)
             if (area != 0.0) {
                 int sx, sy;
                 mod_to_src(kp, i, j, sx, sy);
-                const char *row = (const char *)kp.src + (int64_t)(sy - kp.src_y0) * kp.src_pitch;
+                const char *row = src_base(kp) + (int64_t)(sy - kp.src_y0) * kp.src_pitch;
                 sumA += area;
 #pragma unroll
                 for (int ch = 0; ch < NC; ++ch) acc[ch] += SrcLoad<TI>::get(row, sx * NC + ch) * area;
             }
         }
     }
-    char *drow = (char *)kp.dst + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
+    char *drow = dst_base(kp) + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
     const bool ok = DBL_EPSILON < fabs(sumA);
 #pragma unroll
     for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, ok ? acc[ch] / sumA : 0.0);
@@ -114,7 +114,7 @@ __device__ __forceinline__ void pixel_fast_f64(const AaiKernelParams &kp, int x,
             if (fabs(u0) <= kp.shape.half && fabs(v0) <= kp.shape.half) {  // closed point-in-square (837-864)
                 int sx, sy;
                 mod_to_src(kp, i, j, sx, sy);
-                const char *row = (const char *)kp.src + (int64_t)(sy - kp.src_y0) * kp.src_pitch;
+                const char *row = src_base(kp) + (int64_t)(sy - kp.src_y0) * kp.src_pitch;
                 count += 1;
 #pragma unroll
                 for (int ch = 0; ch < NC; ++ch) acc[ch] += SrcLoad<TI>::get(row, sx * NC + ch);
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H) fast_kernel(const __grid_const
     int count;
     double acc[NC];
     pixel_fast_f64<TI, NC>(kp, x, y, count, acc);
-    char *drow = (char *)kp.dst + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
+    char *drow = dst_base(kp) + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
 #pragma unroll
     for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, count > 0 ? acc[ch] / (double)count : 0.0);
 }
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H) fast_kernel_f32(const __grid_c
     for (int j = jy0; j <= jy1; ++j) {
         const float ry = (float)(j - iry) - fy;
         const float ur = -ry * g.sn, vr = ry * g.cs;
-        const char *rowp = (const char *)kp.src + (int64_t)(j - kp.src_y0) * kp.src_pitch + (int64_t)ix0 * ESZ;  // ident only
+        const char *rowp = src_base(kp) + (int64_t)(j - kp.src_y0) * kp.src_pitch + (int64_t)ix0 * ESZ;  // ident only
         float rx = rx0;
         for (int i = ix0; i <= ix1; ++i, rx += 1.0f, rowp += ESZ) {
             const float mu = g.half - fabsf(fmaf(rx, g.cs, ur));
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H) fast_kernel_f32(const __grid_c
                 if (!ident) {
                     int sx, sy;
                     mod_to_src(kp, i, j, sx, sy);
-                    p = (const char *)kp.src + (int64_t)(sy - kp.src_y0) * kp.src_pitch + (int64_t)sx * ESZ;
+                    p = src_base(kp) + (int64_t)(sy - kp.src_y0) * kp.src_pitch + (int64_t)sx * ESZ;
                 }
                 count += 1.0f;
 #pragma unroll
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H) fast_kernel_f32(const __grid_c
             }
         }
     }
-    char *drow = (char *)kp.dst + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
+    char *drow = dst_base(kp) + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
     if (worst < tau) {  // a centre within the guard band of a footprint edge: FP64 decides
         int c64;
         double a64[NC];
@@ -244,7 +244,7 @@ cudaError_t launch_typed(KernelKind kind, const AaiKernelParams &kp, cudaStream_
     const int rows = kp.row1 - kp.row0;
     if (rows <= 0 || kp.dst_w <= 0) return cudaSuccess;
     dim3 block(TILE_W, TILE_H);
-    dim3 grid((kp.dst_w + TILE_W - 1) / TILE_W, (rows + TILE_H - 1) / TILE_H);
+    dim3 grid((kp.dst_w + TILE_W - 1) / TILE_W, (rows + TILE_H - 1) / TILE_H, kp.batch > 1 ? kp.batch : 1);
     switch (kind) {
         case K_OVERLAP: overlap_kernel_f64<TI, TO, NC><<<grid, block, 0, stream>>>(kp); break;
         case K_SEPARABLE: separable_kernel_f64<TI, TO, NC><<<grid, block, 0, stream>>>(kp); break;

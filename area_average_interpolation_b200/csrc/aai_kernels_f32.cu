@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
     const int ix0 = max(0, bx0), ix1 = min(kp.mod_w - 1, bx1), jy0 = max(0, by0), jy1 = min(kp.mod_h - 1, by1);
     const bool border = bx0 < 0 || by0 < 0 || bx1 > kp.mod_w - 1 || by1 > kp.mod_h - 1;
     const int ncols = ix1 - ix0 + 1, nrows = jy1 - jy0 + 1;
-    char *drow = (char *)kp.dst + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
+    char *drow = dst_base(kp) + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
     if (ncols <= 0 || nrows <= 0) {  // footprint bounding box misses the image: the reference writes 0 (577)
 #pragma unroll
         for (int ch = 0; ch < NC; ++ch) store_f<TO>(drow, x * NC + ch, 0.0f);
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         aai_chord_h_f32(g, t0, xlT, xrT);
         const float e0 = rx0 - 0.5f;  // left boundary of column 0
         constexpr int ESZ = (int)sizeof(TI) * NC;
-        const char *rowp0 = (const char *)kp.src + (int64_t)(jy0 - kp.src_y0) * kp.src_pitch + (int64_t)ix0 * ESZ;
+        const char *rowp0 = src_base(kp) + (int64_t)(jy0 - kp.src_y0) * kp.src_pitch + (int64_t)ix0 * ESZ;
         const char *rowp = rowp0;
         // General path: expanded pixel (i,j) -> source pixel is separable (one source coordinate depends on the
         // column only, the other on the row only; which one is swapped for quadrants 1/3), so the byte offset is
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             if (IDENT)
                 rowp = rowp0 + (int64_t)r * kp.src_pitch;
             else
-                rowp = (const char *)kp.src + row_off(jy0 + r);
+                rowp = src_base(kp) + row_off(jy0 + r);
 #pragma unroll
             for (int k = 0; k < MAXN; ++k) {
 #pragma unroll
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             if (PREFETCH) {
                 if (r + 1 < nrows) fetch(r + 1, nxt);
             } else if (!GROUPED) {
-                rowp = IDENT ? rowp0 + (int64_t)r * kp.src_pitch : (const char *)kp.src + row_off(jy0 + r);
+                rowp = IDENT ? rowp0 + (int64_t)r * kp.src_pitch : src_base(kp) + row_off(jy0 + r);
             }
             float rowA = 0.0f, rowB = 0.0f;  // GROUPED: this row's area in the first / second source column
             const bool top = (rowTop >> r) & 1u;
@@ -306,8 +306,8 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                     p0 = rowp0 + (int64_t)r * kp.src_pitch + (int64_t)k * ESZ;
                     p1 = p0 + minor_stride;
                 } else {
-                    p0 = (const char *)kp.src + row_off(jy0 + r) + col_off(ix0 + k);
-                    p1 = (const char *)kp.src + row_off(jy0 + r + (g.steep ? 0 : 1)) + col_off(ix0 + k + (g.steep ? 1 : 0));
+                    p0 = src_base(kp) + row_off(jy0 + r) + col_off(ix0 + k);
+                    p1 = src_base(kp) + row_off(jy0 + r + (g.steep ? 0 : 1)) + col_off(ix0 + k + (g.steep ? 1 : 0));
                 }
                 sumA += d_before + d_after;
 #pragma unroll
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         }
         if (GROUPED) {  // the (at most) four source pixels, once each
             const int64_t roff0 = row_off(jy0), roffL = row_off(jy1), coff0 = col_off(ix0), coffL = col_off(ix1);
-            const char *base = (const char *)kp.src;
+            const char *base = src_base(kp);
             const char *p00 = base + roff0 + coff0, *p01 = base + roff0 + coffL;
             const char *p10 = base + roffL + coff0, *p11 = base + roffL + coffL;
 #pragma unroll
@@ -363,7 +363,7 @@ cudaError_t launch3(const AaiKernelParams &kp, cudaStream_t stream) {
     const int rows = kp.row1 - kp.row0;
     if (rows <= 0 || kp.dst_w <= 0) return cudaSuccess;
     dim3 block(TILE_W, TILE_H);
-    dim3 grid((kp.dst_w + TILE_W - 1) / TILE_W, (rows + TILE_H - 1) / TILE_H);
+    dim3 grid((kp.dst_w + TILE_W - 1) / TILE_W, (rows + TILE_H - 1) / TILE_H, kp.batch > 1 ? kp.batch : 1);
     if (kp.scale == 1 && kp.quadrant == 0)
         overlap_kernel_f32<TI, TO, NC, ADDR_IDENT><<<grid, block, 0, stream>>>(kp);
     else if (MAXN == 4 && kp.scale >= MAXN - 1)

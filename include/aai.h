@@ -175,10 +175,12 @@ int aai_measure_fp32_tflops(int device, double *tflops);
 int aai_run_device(const aai_plan *plan, int mode, int arith, const aai_image *src, const aai_image *dst,
                    int64_t row0, int64_t row1, int device, void *stream);
 
-/* A batch of images that share one plan (BASELINE config 5: 256 slices).  When the images are whole, single-channel,
- * equally strided in memory (srcs[k].data = srcs[0].data + k*stride, same for dsts) and the plan is axis-aligned,
- * the whole batch is ONE kernel launch (rank-3 TMA tensor map, one grid row per image); otherwise the images are
- * enqueued one after the other.  Device images, asynchronous on `stream`. */
+/* A batch of images that share one plan (BASELINE config 5: 256 slices; the slices of a CT volume under one rotation).
+ * When the images are whole and equally strided in memory (srcs[k].data = srcs[0].data + k*stride, same for dsts;
+ * same pitch, dtype and channel count) the whole batch is ONE kernel launch: the TMA-staged separable kernel takes the
+ * stack as a rank-3 tensor map (one grid row per image), every other kernel of the path (FP32 / FP64 overlap kernels,
+ * fast mode, direct-tap separable) runs with grid.z = image.  Otherwise the images are enqueued one after the other.
+ * Results are bitwise identical to per-image aai_run_device calls.  Device images, asynchronous on `stream`. */
 int aai_run_device_batch(const aai_plan *plan, int mode, int arith, const aai_image *srcs, const aai_image *dsts,
                          int n_images, int device, void *stream);
 

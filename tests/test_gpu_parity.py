@@ -337,13 +337,62 @@ def test_batch_of_slices_is_one_launch_and_matches_per_image_runs(aai, oracle):
     assert torch.equal(dst, ref)
     st, want, _ = oracle.run(src[3].cpu().numpy(), 1.0, 0.5, (100.0, 84.0), 0.0)
     assert (np.abs(dst[3].cpu().numpy() - want) <= TOL_F32_REL * np.maximum(np.abs(want), 1e-30)).all()
-    # not equally strided (reversed order) or rotated: falls back to one launch per image, same results
+    # not equally strided (reversed order): falls back to one launch per image, same results
     order = [4, 2, 0]
     out2 = torch.empty(3, plan.dst_h, plan.dst_w, dtype=torch.float32, device="cuda")
     aai.run_device_batch(plan, [aai.tensor_image(src[k]) for k in order], [aai.tensor_image(out2[i]) for i in range(3)],
                          arith=aai.ARITH_F32, stream=stream)
     torch.cuda.synchronize()
     assert torch.equal(out2, ref[order])
+
+
+@pytest.mark.parametrize("ratio,angle,iso,dtype,ch,mode,arith", [
+    (0.37, 17.3, (60.0, 50.0), "float32", 1, 1, 1),   # FP32 overlap kernel, identity addressing
+    (0.37, 117.3, (60.0, 50.0), "float32", 1, 1, 1),  # rotated quadrant: general addressing
+    (1.7, 40.0, (59.5, 50.5), "uint8", 3, 1, 1),      # upscaling, RGB: grouped path
+    (0.6, 30.0, (60.0, 50.0), "float64", 1, 1, 0),    # unrolled FP64 kernel
+    (0.9, 61.0, (10.0, 20.0), "float32", 2, 1, 0),    # two channels: rolled FP64 kernel
+    (0.37, 30.0, (60.0, 50.0), "float32", 1, 2, 1),   # fast mode, FP32
+    (0.37, 30.0, (60.0, 50.0), "float64", 1, 2, 0),   # fast mode, FP64
+    (0.37, 17.3, (60.0, 50.0), "float32", 1, 3, 1),   # exact mode
+    (2.0, 90.0, (60.0, 50.0), "float32", 1, 1, 1),    # axis-aligned outside the TMA kernel's preconditions: direct taps
+])
+def test_batch_of_rotated_slices_is_one_launch(aai, oracle, ratio, angle, iso, dtype, ch, mode, arith):
+    """A stack of equally strided slices sharing a ROTATED plan (a CT volume) is one launch with grid.z = slice for
+    every kernel of the path, bitwise identical to per-slice launches and within tolerance of the oracle."""
+    import torch
+
+    n, w, h = 4, 120, 100
+    tdt = {"float32": torch.float32, "float64": torch.float64, "uint8": torch.uint8}[dtype]
+    plan = aai.make_plan(w, h, 1.0, ratio, iso, angle)
+    tail = (ch,) if ch > 1 else ()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    if dtype == "uint8":
+        src = torch.randint(0, 256, (n, h, w) + tail, dtype=tdt, device="cuda", generator=g)
+    else:
+        src = (torch.rand((n, h, w) + tail, dtype=torch.float32, device="cuda", generator=g) * 4096).to(tdt)
+    odt = torch.float64 if dtype == "float64" else torch.float32
+    dst = torch.full((n, plan.dst_h, plan.dst_w) + tail, -1.0, dtype=odt, device="cuda")
+    ref = torch.full_like(dst, -2.0)
+    stream = torch.cuda.current_stream().cuda_stream
+    before = aai.launch_count()
+    aai.run_device_batch(plan, [aai.tensor_image(src[k]) for k in range(n)], [aai.tensor_image(dst[k]) for k in range(n)],
+                         mode=mode, arith=arith, stream=stream)
+    assert aai.launch_count() == before + 1
+    for k in range(n):
+        aai.run_device(plan, aai.tensor_image(src[k]), aai.tensor_image(ref[k]), mode=mode, arith=arith, stream=stream)
+    torch.cuda.synchronize()
+    assert torch.equal(dst, ref)
+    if mode != 3:  # (exact mode has its own checker, test_exact_mode_matches_its_clipping_checker)
+        k = n - 1
+        plane = src[k].cpu().numpy().astype(np.float64)
+        got = dst[k].cpu().numpy().astype(np.float64)
+        for c in range(ch):
+            st, want, _ = oracle.run(plane[..., c] if ch > 1 else plane, 1.0, ratio, iso, angle, mode=mode)
+            assert st == 0
+            tol = TOL_F32_REL if arith == 1 else TOL_F64_REL
+            gc = got[..., c] if ch > 1 else got
+            assert (np.abs(gc - want) <= tol * np.maximum(np.abs(want), 1.0)).all()
 
 
 def test_device_image_helpers_roundtrip(aai):
