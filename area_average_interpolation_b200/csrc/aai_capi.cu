@@ -453,16 +453,25 @@ int aai_run_device_batch(const aai_plan *plan, int mode, int arith, const aai_im
                 a.rows == a.height && b.width == d0.width && b.height == d0.height && b.y0 == 0 &&
                 b.rows == b.height && a.channels == s0.channels && b.channels == d0.channels;
     }
-    if (stack && sstride > 0 && dstride > 0) {
+    // (the grid.z kernels address the stack as one tall image: strides must be whole rows)
+    if (stack && sstride > 0 && dstride > 0 && sstride % s0.pitch_bytes == 0 && dstride % d0.pitch_bytes == 0 &&
+        sstride / s0.pitch_bytes < (1 << 30) && dstride / d0.pitch_bytes < (1 << 30)) {
         AAI_CUDA(cudaSetDevice(device));
-        constexpr int kMaxGridZ = 65535;
-        for (int first = 0; first < n_images; first += kMaxGridZ) {
-            const int n = n_images - first < kMaxGridZ ? n_images - first : kMaxGridZ;
+        const int64_t srows = sstride / s0.pitch_bytes, drows = dstride / d0.pitch_bytes;
+        // images per launch: grid.y / grid.z limit, and row indices of the stack must stay below 2^31
+        int64_t per_launch = 65535;
+        const int64_t most_rows = srows > drows ? srows : drows;
+        if (per_launch * most_rows > 0x7fffffffLL) per_launch = 0x7fffffffLL / most_rows;
+        if (per_launch < 1) per_launch = 1;
+        for (int first = 0; first < n_images; first += (int)per_launch) {
+            const int n = n_images - first < per_launch ? n_images - first : (int)per_launch;
             AaiKernelParams kp = aai_make_kernel_params(*plan, srcs[first], dsts[first], 0, plan->dst_h);
             kp.quirk = mode == AAI_MODE_AREA_AVERAGE_EXACT ? 0 : 1;
             kp.batch = n;
             kp.src_batch_stride = sstride;
             kp.dst_batch_stride = dstride;
+            kp.src_batch_rows = (int32_t)srows;
+            kp.dst_batch_rows = (int32_t)drows;
             int e;
             if (mode == AAI_MODE_FAST)
                 e = aai_launch_fast(kp, arith, s0.dtype, d0.dtype, stream);

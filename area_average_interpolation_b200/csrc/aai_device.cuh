@@ -61,12 +61,15 @@ __device__ __forceinline__ void store_dst<uint8_t>(void *row, int idx, double v)
 }
 
 // Batched launches: gridDim.z = the images of an equally strided stack that share one plan (aai_run_device_batch);
-// blockIdx.z selects this CTA's image.  Single-image launches have gridDim.z = 1 and stride 0.
-__device__ __forceinline__ const char *src_base(const AaiKernelParams &kp) {
-    return (const char *)kp.src + (int64_t)blockIdx.z * kp.src_batch_stride;
+// blockIdx.z selects this CTA's image.  The stack is addressed as ONE tall image -- image k's row r is row
+// r + k * batch_rows of the stack -- so the batch costs one integer multiply-add per base row instead of 64-bit pointer
+// arithmetic (the FP32 overlap kernel is issue-bound: every instruction per pixel shows).  Single-image launches have
+// gridDim.z = 1 and batch_rows = 0.
+__device__ __forceinline__ int src_row0(const AaiKernelParams &kp) {
+    return kp.src_y0 - (int)blockIdx.z * kp.src_batch_rows;
 }
-__device__ __forceinline__ char *dst_base(const AaiKernelParams &kp) {
-    return (char *)kp.dst + (int64_t)blockIdx.z * kp.dst_batch_stride;
+__device__ __forceinline__ int dst_row0(const AaiKernelParams &kp) {
+    return kp.dst_y0 - (int)blockIdx.z * kp.dst_batch_rows;
 }
 
 // expanded + quadrant-rotated pixel (mx,my) -> original source pixel (inverse of Source.cpp:163-168)
@@ -138,7 +141,7 @@ __device__ __forceinline__ void pixel_f64(const AaiKernelParams &kp, double cx, 
             if (area != 0.0) {
                 int sx, sy;
                 mod_to_src(kp, i, j, sx, sy);
-                const char *row = src_base(kp) + (int64_t)(sy - kp.src_y0) * kp.src_pitch;
+                const char *row = (const char *)kp.src + (int64_t)(sy - src_row0(kp)) * kp.src_pitch;
                 sumA += area;
 #pragma unroll
                 for (int ch = 0; ch < NC; ++ch) acc[ch] += SrcLoad<TI>::get(row, sx * NC + ch) * area;

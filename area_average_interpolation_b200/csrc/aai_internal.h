@@ -39,7 +39,8 @@ struct AaiKernelParams {
     // batch of equally strided images sharing one plan (0/1 = single image): blockIdx.y of the separable TMA kernel,
     // blockIdx.z of every other kernel selects the image
     int32_t batch;
-    int64_t src_batch_stride, dst_batch_stride;
+    int64_t src_batch_stride, dst_batch_stride;  // bytes between consecutive images
+    int32_t src_batch_rows, dst_batch_rows;      // the same in rows of the pitch (grid.z kernels; strides are whole rows)
 };
 
 AaiKernelParams aai_make_kernel_params(const aai_plan &plan, const aai_image &src, const aai_image &dst,

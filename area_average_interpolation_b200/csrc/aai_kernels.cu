@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H)
     cell_range(kp, cx, cy, ix0, ix1, jy0, jy1);
     double sumA, acc[NC];
     pixel_f64<TI, NC>(kp, cx, cy, ix0, ix1, jy0, jy1, sumA, acc);
-    char *drow = dst_base(kp) + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
+    char *drow = (char *)kp.dst + (int64_t)(y - dst_row0(kp)) * kp.dst_pitch;
     const bool ok = DBL_EPSILON < fabs(sumA);  // Source.cpp:577
 #pragma unroll
     for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, ok ? acc[ch] / sumA : 0.0);
@@ -76,14 +76,14 @@ __global__ void __launch_bounds__(TILE_W *TILE_H)
             if (area != 0.0) {
                 int sx, sy;
                 mod_to_src(kp, i, j, sx, sy);
-                const char *row = src_base(kp) + (int64_t)(sy - kp.src_y0) * kp.src_pitch;
+                const char *row = (const char *)kp.src + (int64_t)(sy - src_row0(kp)) * kp.src_pitch;
                 sumA += area;
 #pragma unroll
                 for (int ch = 0; ch < NC; ++ch) acc[ch] += SrcLoad<TI>::get(row, sx * NC + ch) * area;
             }
         }
     }
-    char *drow = dst_base(kp) + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
+    char *drow = (char *)kp.dst + (int64_t)(y - dst_row0(kp)) * kp.dst_pitch;
     const bool ok = DBL_EPSILON < fabs(sumA);
 #pragma unroll
     for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, ok ? acc[ch] / sumA : 0.0);
@@ -114,7 +114,7 @@ __device__ __forceinline__ void pixel_fast_f64(const AaiKernelParams &kp, int x,
             if (fabs(u0) <= kp.shape.half && fabs(v0) <= kp.shape.half) {  // closed point-in-square (837-864)
                 int sx, sy;
                 mod_to_src(kp, i, j, sx, sy);
-                const char *row = src_base(kp) + (int64_t)(sy - kp.src_y0) * kp.src_pitch;
+                const char *row = (const char *)kp.src + (int64_t)(sy - src_row0(kp)) * kp.src_pitch;
                 count += 1;
 #pragma unroll
                 for (int ch = 0; ch < NC; ++ch) acc[ch] += SrcLoad<TI>::get(row, sx * NC + ch);
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H) fast_kernel(const __grid_const
     int count;
     double acc[NC];
     pixel_fast_f64<TI, NC>(kp, x, y, count, acc);
-    char *drow = dst_base(kp) + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
+    char *drow = (char *)kp.dst + (int64_t)(y - dst_row0(kp)) * kp.dst_pitch;
 #pragma unroll
     for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, count > 0 ? acc[ch] / (double)count : 0.0);
 }
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H) fast_kernel_f32(const __grid_c
     for (int j = jy0; j <= jy1; ++j) {
         const float ry = (float)(j - iry) - fy;
         const float ur = -ry * g.sn, vr = ry * g.cs;
-        const char *rowp = src_base(kp) + (int64_t)(j - kp.src_y0) * kp.src_pitch + (int64_t)ix0 * ESZ;  // ident only
+        const char *rowp = (const char *)kp.src + (int64_t)(j - src_row0(kp)) * kp.src_pitch + (int64_t)ix0 * ESZ;  // ident only
         float rx = rx0;
         for (int i = ix0; i <= ix1; ++i, rx += 1.0f, rowp += ESZ) {
             const float mu = g.half - fabsf(fmaf(rx, g.cs, ur));
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H) fast_kernel_f32(const __grid_c
                 if (!ident) {
                     int sx, sy;
                     mod_to_src(kp, i, j, sx, sy);
-                    p = src_base(kp) + (int64_t)(sy - kp.src_y0) * kp.src_pitch + (int64_t)sx * ESZ;
+                    p = (const char *)kp.src + (int64_t)(sy - src_row0(kp)) * kp.src_pitch + (int64_t)sx * ESZ;
                 }
                 count += 1.0f;
 #pragma unroll
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H) fast_kernel_f32(const __grid_c
             }
         }
     }
-    char *drow = dst_base(kp) + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
+    char *drow = (char *)kp.dst + (int64_t)(y - dst_row0(kp)) * kp.dst_pitch;
     if (worst < tau) {  // a centre within the guard band of a footprint edge: FP64 decides
         int c64;
         double a64[NC];

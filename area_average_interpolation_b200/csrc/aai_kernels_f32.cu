@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
     const int ix0 = max(0, bx0), ix1 = min(kp.mod_w - 1, bx1), jy0 = max(0, by0), jy1 = min(kp.mod_h - 1, by1);
     const bool border = bx0 < 0 || by0 < 0 || bx1 > kp.mod_w - 1 || by1 > kp.mod_h - 1;
     const int ncols = ix1 - ix0 + 1, nrows = jy1 - jy0 + 1;
-    char *drow = dst_base(kp) + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
+    char *drow = (char *)kp.dst + (int64_t)(y - dst_row0(kp)) * kp.dst_pitch;
     if (ncols <= 0 || nrows <= 0) {  // footprint bounding box misses the image: the reference writes 0 (577)
 #pragma unroll
         for (int ch = 0; ch < NC; ++ch) store_f<TO>(drow, x * NC + ch, 0.0f);
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         aai_chord_h_f32(g, t0, xlT, xrT);
         const float e0 = rx0 - 0.5f;  // left boundary of column 0
         constexpr int ESZ = (int)sizeof(TI) * NC;
-        const char *rowp0 = src_base(kp) + (int64_t)(jy0 - kp.src_y0) * kp.src_pitch + (int64_t)ix0 * ESZ;
+        const char *rowp0 = (const char *)kp.src + (int64_t)(jy0 - src_row0(kp)) * kp.src_pitch + (int64_t)ix0 * ESZ;
         const char *rowp = rowp0;
         // General path: expanded pixel (i,j) -> source pixel is separable (one source coordinate depends on the
         // column only, the other on the row only; which one is swapped for quadrants 1/3), so the byte offset is
@@ -140,12 +140,12 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             return (int64_t)(kp.scale != 1 ? __umulhi((unsigned)e, kp.div_magic) : (unsigned)e);
         };
         auto col_off = [&](int i) -> int64_t {
-            return swapped ? (div_s(kp.e_ayi * i + kp.e_ay0) - kp.src_y0) * kp.src_pitch
+            return swapped ? (div_s(kp.e_ayi * i + kp.e_ay0) - src_row0(kp)) * kp.src_pitch
                            : div_s(kp.e_axi * i + kp.e_ax0) * ESZ;
         };
         auto row_off = [&](int j) -> int64_t {
             return swapped ? div_s(kp.e_axj * j + kp.e_ax0) * ESZ
-                           : (div_s(kp.e_ayj * j + kp.e_ay0) - kp.src_y0) * kp.src_pitch;
+                           : (div_s(kp.e_ayj * j + kp.e_ay0) - src_row0(kp)) * kp.src_pitch;
         };
         int64_t coff[MAXN];
         if (!IDENT && !GROUPED) {
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             if (IDENT)
                 rowp = rowp0 + (int64_t)r * kp.src_pitch;
             else
-                rowp = src_base(kp) + row_off(jy0 + r);
+                rowp = (const char *)kp.src + row_off(jy0 + r);
 #pragma unroll
             for (int k = 0; k < MAXN; ++k) {
 #pragma unroll
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             if (PREFETCH) {
                 if (r + 1 < nrows) fetch(r + 1, nxt);
             } else if (!GROUPED) {
-                rowp = IDENT ? rowp0 + (int64_t)r * kp.src_pitch : src_base(kp) + row_off(jy0 + r);
+                rowp = IDENT ? rowp0 + (int64_t)r * kp.src_pitch : (const char *)kp.src + row_off(jy0 + r);
             }
             float rowA = 0.0f, rowB = 0.0f;  // GROUPED: this row's area in the first / second source column
             const bool top = (rowTop >> r) & 1u;
@@ -306,8 +306,8 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                     p0 = rowp0 + (int64_t)r * kp.src_pitch + (int64_t)k * ESZ;
                     p1 = p0 + minor_stride;
                 } else {
-                    p0 = src_base(kp) + row_off(jy0 + r) + col_off(ix0 + k);
-                    p1 = src_base(kp) + row_off(jy0 + r + (g.steep ? 0 : 1)) + col_off(ix0 + k + (g.steep ? 1 : 0));
+                    p0 = (const char *)kp.src + row_off(jy0 + r) + col_off(ix0 + k);
+                    p1 = (const char *)kp.src + row_off(jy0 + r + (g.steep ? 0 : 1)) + col_off(ix0 + k + (g.steep ? 1 : 0));
                 }
                 sumA += d_before + d_after;
 #pragma unroll
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         }
         if (GROUPED) {  // the (at most) four source pixels, once each
             const int64_t roff0 = row_off(jy0), roffL = row_off(jy1), coff0 = col_off(ix0), coffL = col_off(ix1);
-            const char *base = src_base(kp);
+            const char *base = (const char *)kp.src;
             const char *p00 = base + roff0 + coff0, *p01 = base + roff0 + coffL;
             const char *p10 = base + roffL + coff0, *p11 = base + roffL + coffL;
 #pragma unroll

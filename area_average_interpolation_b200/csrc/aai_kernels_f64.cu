@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 512 / (TILE_W *TILE_H))
     int ix0, ix1, jy0, jy1;
     const bool border = cell_range(kp, cx, cy, ix0, ix1, jy0, jy1);
     const int ncols = ix1 - ix0 + 1, nrows = jy1 - jy0 + 1;
-    char *drow = dst_base(kp) + (int64_t)(y - kp.dst_y0) * kp.dst_pitch;
+    char *drow = (char *)kp.dst + (int64_t)(y - dst_row0(kp)) * kp.dst_pitch;
     if (ncols <= 0 || nrows <= 0) {  // footprint bounding box misses the image: the reference writes 0 (577)
 #pragma unroll
         for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, 0.0);
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 512 / (TILE_W *TILE_H))
 #pragma unroll
         for (int k = 0; k <= MAXN; ++k) cv[k] = aai_clamp_chord(t0, yt[k], yb[k]);
         constexpr int ESZ = (int)sizeof(TI) * NC;
-        const char *rowp0 = src_base(kp) + (int64_t)(jy0 - kp.src_y0) * kp.src_pitch + (int64_t)ix0 * ESZ;
+        const char *rowp0 = (const char *)kp.src + (int64_t)(jy0 - src_row0(kp)) * kp.src_pitch + (int64_t)ix0 * ESZ;
         // General frame: expanded pixel (i,j) -> source pixel is separable (one source coordinate depends on the column
         // only, the other on the row only; swapped for quadrants 1/3): byte offset = col_off(i) + row_off(j), the column
         // parts hoisted out of the row loop (as in the FP32 kernel).
@@ -76,12 +76,12 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 512 / (TILE_W *TILE_H))
             return (int64_t)(kp.scale != 1 ? __umulhi((unsigned)e, kp.div_magic) : (unsigned)e);
         };
         auto col_off = [&](int i) -> int64_t {
-            return swapped ? (div_s(kp.e_ayi * i + kp.e_ay0) - kp.src_y0) * kp.src_pitch
+            return swapped ? (div_s(kp.e_ayi * i + kp.e_ay0) - src_row0(kp)) * kp.src_pitch
                            : div_s(kp.e_axi * i + kp.e_ax0) * ESZ;
         };
         auto row_off = [&](int j) -> int64_t {
             return swapped ? div_s(kp.e_axj * j + kp.e_ax0) * ESZ
-                           : (div_s(kp.e_ayj * j + kp.e_ay0) - kp.src_y0) * kp.src_pitch;
+                           : (div_s(kp.e_ayj * j + kp.e_ay0) - src_row0(kp)) * kp.src_pitch;
         };
         int64_t coff[MAXN];
         if (!IDENT) {
@@ -90,10 +90,10 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 512 / (TILE_W *TILE_H))
         }
         auto cell_ptr = [&](int k, int r) -> const char * {  // source element of cell (column k, row r), any k
             if (IDENT) return rowp0 + (int64_t)r * kp.src_pitch + (int64_t)k * ESZ;
-            return src_base(kp) + row_off(jy0 + r) + col_off(ix0 + k);
+            return (const char *)kp.src + row_off(jy0 + r) + col_off(ix0 + k);
         };
         for (int r = 0; r < nrows; ++r) {
-            const char *rowp = IDENT ? rowp0 + (int64_t)r * kp.src_pitch : src_base(kp) + row_off(jy0 + r);
+            const char *rowp = IDENT ? rowp0 + (int64_t)r * kp.src_pitch : (const char *)kp.src + row_off(jy0 + r);
             const double ry = ry0 + (double)r;
             double xlB, xrB;
             aai_chord_h(g, ry + 0.5, xlB, xrB);

@@ -371,7 +371,7 @@ def test_batch_of_rotated_slices_is_one_launch(aai, oracle, ratio, angle, iso, d
         src = torch.randint(0, 256, (n, h, w) + tail, dtype=tdt, device="cuda", generator=g)
     else:
         src = (torch.rand((n, h, w) + tail, dtype=torch.float32, device="cuda", generator=g) * 4096).to(tdt)
-    odt = torch.float64 if dtype == "float64" else torch.float32
+    odt = torch.float64 if arith == 0 else torch.float32  # (a float32 store would round the FP64 result)
     dst = torch.full((n, plan.dst_h, plan.dst_w) + tail, -1.0, dtype=odt, device="cuda")
     ref = torch.full_like(dst, -2.0)
     stream = torch.cuda.current_stream().cuda_stream
