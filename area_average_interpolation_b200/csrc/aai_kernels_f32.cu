@@ -33,6 +33,14 @@ constexpr int MAXN = AAI_MAXN;
 #define AAI_ROW_UNROLL 1
 #endif
 constexpr int kRowUnroll = AAI_ROW_UNROLL;
+// Columns that every interior footprint of this translation unit touches: a footprint box of side 2 ext holds at least
+// floor(2 ext) lattice columns, and the host picks MAXN = floor(2 ext) + 1 (MAXN = 8 also serves floor(2 ext) = 6).
+// Their loads need no predicate; a pixel whose FP32 cell range comes out narrower (2 ext within rounding of an integer)
+// takes the FP64 path.
+#ifndef AAI_MINC
+#define AAI_MINC (AAI_MAXN == 8 ? 6 : AAI_MAXN - 1)
+#endif
+constexpr int MINC = AAI_MINC;
 
 template <typename T>
 struct LoadF;
@@ -109,7 +117,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
     float worst = 1.0f;
     // Border pixels (footprint partly outside the image) are normalised by a partial, possibly tiny, total area:
     // they need relative accuracy, so they take the FP64 path (~0.1% of a large canvas).
-    bool redo = border || ncols > MAXN || nrows > MAXN;  // (the MAXN test cannot fire for the MAXN the host picked)
+    bool redo = border || ncols > MAXN || nrows > MAXN || ncols < MINC;  // (the MAXN test cannot fire for the MAXN the host picked)
     if (!redo) {
         const AaiShapeF &g = kp.shapef;
         const int dj0 = jy0 - iry;
@@ -186,7 +194,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             for (int k = 0; k < MAXN; ++k) {
 #pragma unroll
                 for (int ch = 0; ch < NC; ++ch) v[k][ch] = 0.0f;
-                if (k < ncols) {  // columns beyond the footprint box are never read (their area is exactly 0)
+                if (k < MINC || k < ncols) {  // columns beyond the footprint box are never read (their area is exactly 0)
                     const char *p = IDENT ? rowp + k * ESZ : rowp + coff[k];
 #pragma unroll
                     for (int ch = 0; ch < NC; ++ch) v[k][ch] = LoadF<TI>::get(p + ch * (int)sizeof(TI));
@@ -219,7 +227,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 } else if (PREFETCH) {
 #pragma unroll
                     for (int ch = 0; ch < NC; ++ch) acc[ch] = fmaf(cur[k][ch], area, acc[ch]);
-                } else if (k < ncols) {  // load at the point of use
+                } else if (k < MINC || k < ncols) {  // load at the point of use
                     const char *p = IDENT ? rowp + k * ESZ : rowp + coff[k];
 #pragma unroll
                     for (int ch = 0; ch < NC; ++ch)
