@@ -75,7 +75,10 @@ __device__ __forceinline__ void store_f<uint8_t>(void *row, int idx, float v) {
 // IDENT: scale 1, quadrant 0 (expanded pixel (i,j) IS source pixel (i,j)): constant element stride, offsets fold
 // into the load instruction.  Otherwise the general expanded-frame affine map + division by the scale.
 #ifndef AAI_F32_MIN_BLOCKS
-#define AAI_F32_MIN_BLOCKS ((AAI_MAXN <= 5 ? 896 : 512) / (AAI_TILE_W * AAI_TILE_H))  // 28 resp. 16 warps per SM
+// resident threads per SM the register allocation is bounded for: 28 warps (72 registers) for MAXN = 4, 24 warps (80
+// registers) for MAXN = 5 (measured on config 4 with the final row body: 5/6/7/8 CTAs per SM = 1.562/1.455/1.466/1.529 ms;
+// config 3, MAXN = 4: 6 CTAs 8.19 ms vs 7 CTAs 8.14 ms), 16 warps for the wide footprints
+#define AAI_F32_MIN_BLOCKS ((AAI_MAXN <= 4 ? 896 : AAI_MAXN == 5 ? 768 : 512) / (AAI_TILE_W * AAI_TILE_H))
 #endif
 // ADDR: how a cell finds its source value.
 //   ADDR_GENERAL  expanded + quadrant-rotated frame, separable byte offset col_off(i) + row_off(j)
