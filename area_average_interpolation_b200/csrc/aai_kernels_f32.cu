@@ -34,11 +34,11 @@ constexpr int MAXN = AAI_MAXN;
 #endif
 constexpr int kRowUnroll = AAI_ROW_UNROLL;
 // Columns that every interior footprint of this translation unit touches: a footprint box of side 2 ext holds at least
-// floor(2 ext) lattice columns, and the host picks MAXN = floor(2 ext) + 1 (MAXN = 8 also serves floor(2 ext) = 6).
-// Their loads need no predicate; a pixel whose FP32 cell range comes out narrower (2 ext within rounding of an integer)
-// takes the FP64 path.
+// floor(2 ext) lattice columns, and the host picks the smallest MAXN >= floor(2 ext) + 1 (MAXN = 8 also serves
+// floor(2 ext) = 6, MAXN = 4 also floor(2 ext) = 2: L(c+s) < 2).  Their loads need no predicate; a pixel whose FP32 cell
+// range comes out narrower (2 ext within rounding of an integer) takes the FP64 path.
 #ifndef AAI_MINC
-#define AAI_MINC (AAI_MAXN == 8 ? 6 : AAI_MAXN - 1)
+#define AAI_MINC (AAI_MAXN == 8 ? 6 : AAI_MAXN == 4 ? 2 : AAI_MAXN - 1)
 #endif
 constexpr int MINC = AAI_MINC;
 
