@@ -32,6 +32,12 @@ constexpr int MAXN = AAI_MAXN;
 #ifndef AAI_ROW_UNROLL
 #define AAI_ROW_UNROLL 1
 #endif
+#ifndef AAI_EXP_RY_INC
+#define AAI_EXP_RY_INC 0
+#endif
+#ifndef AAI_EXP_ROW2
+#define AAI_EXP_ROW2 0
+#endif
 constexpr int kRowUnroll = AAI_ROW_UNROLL;
 // Columns that every interior footprint of this translation unit touches: a footprint box of side 2 ext holds at least
 // floor(2 ext) lattice columns, and the host picks the smallest MAXN >= floor(2 ext) + 1 (MAXN = 8 also serves
@@ -187,7 +193,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         // row r are computed): the accumulate at the end of a row never waits for its own row's loads.
         // (Single-channel kernels only: three channels would need 30 staging registers.)
         constexpr bool PREFETCH = NC == 1 && !GROUPED;
-        float cur[MAXN][NC];
+        float buf[MAXN][NC];
         auto fetch = [&](int r, float (&v)[MAXN][NC]) {
             if (IDENT)
                 rowp = rowp0 + (int64_t)r * kp.src_pitch;
@@ -204,10 +210,12 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 }
             }
         };
-        if (PREFETCH) fetch(0, cur);
-#pragma unroll kRowUnroll
-        for (int r = 0; r < nrows; ++r) {
-            float nxt[MAXN][NC];
+        if (PREFETCH) fetch(0, buf);
+#if AAI_EXP_RY_INC
+        float ry_run = (float)dj0 - fy;
+#endif
+        // one row of cells: `cur` holds this row's source values (PREFETCH), `nxt` receives the next row's
+        auto row = [&](int r, float (&cur)[MAXN][NC], float (&nxt)[MAXN][NC]) {
             if (PREFETCH) {
                 if (r + 1 < nrows) fetch(r + 1, nxt);
             } else if (!GROUPED) {
@@ -215,7 +223,12 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             }
             float rowA = 0.0f, rowB = 0.0f;  // GROUPED: this row's area in the first / second source column
             const bool top = (rowTop >> r) & 1u;
+#if AAI_EXP_RY_INC  // experiment (default off): carried row offset, one FADD instead of I2F + FADD
+            const float ry = ry_run;
+            ry_run += 1.0f;
+#else
             const float ry = (float)(dj0 + r) - fy;
+#endif
             float xlB, xrB;
             aai_chord_h_f32(g, ry + 0.5f, xlB, xrB);
             const float ey = ry - 0.5f;
@@ -276,13 +289,26 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 W10 += top ? 0.0f : rowA;
                 W11 += top ? 0.0f : rowB;
             }
+        };
+#if AAI_EXP_ROW2  // experiment (default off): two rows per iteration, the two value buffers swap roles
+        float buf2[MAXN][NC];
+        for (int r = 0; r < nrows; r += 2) {
+            row(r, buf, buf2);
+            if (r + 1 < nrows) row(r + 1, buf2, buf);
+        }
+#else
+#pragma unroll kRowUnroll
+        for (int r = 0; r < nrows; ++r) {
+            float nxt[MAXN][NC];
+            row(r, buf, nxt);
             if (PREFETCH) {
 #pragma unroll
                 for (int k = 0; k < MAXN; ++k)
 #pragma unroll
-                    for (int ch = 0; ch < NC; ++ch) cur[k][ch] = nxt[k][ch];
+                    for (int ch = 0; ch < NC; ++ch) buf[k][ch] = nxt[k][ch];
             }
         }
+#endif
         // Total overlap: the exact areas of a footprint inside the image add up to L^2 (border pixels never get here).
         sumA = g.area_total;
         // The reference's shape-2/4 quirk: one pair of corrected cells per minor-axis grid line crossed by a left/right
