@@ -38,6 +38,9 @@ constexpr int MAXN = AAI_MAXN;
 #ifndef AAI_EXP_ROW2
 #define AAI_EXP_ROW2 0
 #endif
+#ifndef AAI_EXP_EDGE_CSE
+#define AAI_EXP_EDGE_CSE 0
+#endif
 constexpr int kRowUnroll = AAI_ROW_UNROLL;
 // Columns that every interior footprint of this translation unit touches: a footprint box of side 2 ext holds at least
 // floor(2 ext) lattice columns, and the host picks the smallest MAXN >= floor(2 ext) + 1 (MAXN = 8 also serves
@@ -135,13 +138,22 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
 #pragma unroll
         for (int k = 0; k + 1 <= MAXN; k += 2) {  // two grid lines per packed instruction
             AaiF2 t2, b2;
+#if AAI_EXP_EDGE_CSE  // experiment (default off): one expression for a column boundary everywhere, so that the boundaries
+                      // of the chords, of the top sides and of the row body are common subexpressions (~10 FADD/pixel)
+            aai_chord_v_f32x2(g, aai_f2((rx0 + (float)k) - 0.5f, (rx0 + (float)(k + 1)) - 0.5f), t2, b2);
+#else
             aai_chord_v_f32x2(g, aai_f2(rx0 + ((float)k - 0.5f), rx0 + ((float)k + 0.5f)), t2, b2);
+#endif
             yt[k] = t2.x;
             yt[k + 1] = t2.y;
             yb[k] = b2.x;
             yb[k + 1] = b2.y;
         }
+#if AAI_EXP_EDGE_CSE
+        if ((MAXN + 1) & 1) aai_chord_v_f32(g, (rx0 + (float)MAXN) - 0.5f, yt[MAXN], yb[MAXN]);
+#else
         if ((MAXN + 1) & 1) aai_chord_v_f32(g, rx0 + ((float)MAXN - 0.5f), yt[MAXN], yb[MAXN]);
+#endif
         float xlT, xrT;  // chord of the footprint on the row's top grid line
         const float t0 = ((float)dj0 - fy) - 0.5f;  // top of row 0
         aai_chord_h_f32(g, t0, xlT, xrT);
@@ -188,7 +200,11 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         // lengths of the cells' top sides inside the footprint: the previous row's bottom sides
         float lenTop[MAXN];
 #pragma unroll
+#if AAI_EXP_EDGE_CSE
+        for (int k = 0; k < MAXN; ++k) lenTop[k] = aai_overlap1_f32(xlT, xrT, (rx0 + (float)k) - 0.5f);
+#else
         for (int k = 0; k < MAXN; ++k) lenTop[k] = aai_overlap1_f32(xlT, xrT, e0 + (float)k);
+#endif
         // Source values are fetched one row ahead of their use (the loads of row r+1 are in flight while the areas of
         // row r are computed): the accumulate at the end of a row never waits for its own row's loads.
         // (Single-channel kernels only: three channels would need 30 staging registers.)
