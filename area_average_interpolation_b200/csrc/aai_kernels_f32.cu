@@ -227,8 +227,10 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             }
         };
         if (PREFETCH) fetch(0, buf);
-#if AAI_EXP_RY_INC
+#if AAI_EXP_RY_INC == 1
         float ry_run = (float)dj0 - fy;
+#elif AAI_EXP_RY_INC == 2
+        float ry_run = (float)dj0;
 #endif
         // one row of cells: `cur` holds this row's source values (PREFETCH), `nxt` receives the next row's
         auto row = [&](int r, float (&cur)[MAXN][NC], float (&nxt)[MAXN][NC]) {
@@ -239,8 +241,11 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             }
             float rowA = 0.0f, rowB = 0.0f;  // GROUPED: this row's area in the first / second source column
             const bool top = (rowTop >> r) & 1u;
-#if AAI_EXP_RY_INC  // experiment (default off): carried row offset, one FADD instead of I2F + FADD
+#if AAI_EXP_RY_INC == 1  // experiment (default off): carried row offset, one FADD instead of I2F + FADD
             const float ry = ry_run;
+            ry_run += 1.0f;
+#elif AAI_EXP_RY_INC == 2  // variant with bit-identical results: the integer row index carried as a float (exact)
+            const float ry = ry_run - fy;
             ry_run += 1.0f;
 #else
             const float ry = (float)(dj0 + r) - fy;
