@@ -121,3 +121,44 @@ def test_no_cpu_fallback_without_a_gpu(aai):
     with pytest.raises(aai.AaiError) as ei:
         op.areaAverageInterpolation(np.ones((8, 8)), 1.0, 0.5, (4, 4), 0.0)
     assert ei.value.status in (aai.ERR_NO_DEVICE, aai.ERR_CUDA)
+
+
+def test_partition_and_halo_properties_on_random_plans(aai):
+    """Host logic of SURVEY 8e on random geometry (all quadrants, up- and downscaling, off-centre isocentres):
+    bands tile the canvas, loads add up, a band's halo contains the halo of every sub-band (what the chunk-pipelined
+    host path uploads progressively), and masking the source outside a band's halo does not change the band."""
+    from oracle import port
+
+    rng = np.random.default_rng(8128)
+    for case in range(24):
+        w, h = int(rng.integers(24, 90)), int(rng.integers(24, 90))
+        ratio = float(rng.choice([0.23, 0.37, 0.5, 0.9, 1.0, 1.7, 2.3]))
+        angle = float(rng.choice([0.0, 90.0, 17.3, 30.0, 61.0, 117.3, 200.0, 305.5, -12.0]))
+        iso = (float(rng.uniform(-10, w + 10)), float(rng.uniform(-10, h + 10)))
+        p = aai.make_plan(w, h, 1.0, ratio, iso, angle)
+        assert p.status == 0
+        if p.dst_h < 4:
+            continue
+        n = int(rng.integers(1, min(6, p.dst_h) + 1))
+        b = aai.partition_rows(p, n)
+        assert b[0] == 0 and b[-1] == p.dst_h and all(b[i] <= b[i + 1] for i in range(n)), (case, b)
+        assert sum(aai.covered_pixels(p, b[i], b[i + 1]) for i in range(n)) == aai.covered_pixels(p)
+        k = int(rng.integers(0, n))
+        r0, r1 = b[k], b[k + 1]
+        if r1 <= r0:
+            continue
+        x0, x1, y0, y1 = aai.band_source_window(p, r0, r1)
+        assert 0 <= x0 <= x1 <= w and 0 <= y0 <= y1 <= h
+        # sub-bands (pipeline chunks) stay inside the band's halo
+        cuts = sorted(set([r0, r1] + [int(v) for v in rng.integers(r0, r1 + 1, size=3)]))
+        for a, c in zip(cuts[:-1], cuts[1:]):
+            sx0, sx1, sy0, sy1 = aai.band_source_window(p, a, c)
+            if sy1 > sy0 and sx1 > sx0:
+                assert x0 <= sx0 and sx1 <= x1 and y0 <= sy0 and sy1 <= y1, (case, a, c)
+        if case % 3 == 0:  # (the oracle runs are the slow part)
+            src = rng.uniform(1.0, 2.0, size=(h, w))
+            st, full, _ = port.run(src, 1.0, ratio, iso, angle, rows=(r0, r1))
+            masked = np.zeros_like(src)
+            masked[y0:y1, x0:x1] = src[y0:y1, x0:x1]
+            st2, got, _ = port.run(masked, 1.0, ratio, iso, angle, rows=(r0, r1))
+            assert st == 0 and st2 == 0 and np.array_equal(got, full), case
