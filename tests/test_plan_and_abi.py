@@ -162,3 +162,33 @@ def test_partition_and_halo_properties_on_random_plans(aai):
             masked[y0:y1, x0:x1] = src[y0:y1, x0:x1]
             st2, got, _ = port.run(masked, 1.0, ratio, iso, angle, rows=(r0, r1))
             assert st == 0 and st2 == 0 and np.array_equal(got, full), case
+
+
+def test_run_entry_points_validate_before_touching_cuda(aai):
+    """Argument errors of the run functions are decided on the host before any CUDA call, so they are the same on a box
+    without a GPU: shapes that do not match the plan, unknown mode / arithmetic, rows outside the band, a failed plan
+    (its status comes back unchanged), an empty batch."""
+    plan = aai.make_plan(64, 48, 1.0, 0.5, (32, 24), 10.0)
+    src = np.zeros((48, 64), dtype=np.float32)
+    dst = np.zeros((plan.dst_h, plan.dst_w), dtype=np.float32)
+    si, di = aai._host_image(src), aai._host_image(dst)
+    small = aai._host_image(np.zeros((5, 5), dtype=np.float32))
+
+    def status_of(fn, *a, **k):
+        with pytest.raises(aai.AaiError) as ei:
+            fn(*a, **k)
+        return ei.value.status
+
+    assert status_of(aai.run_device, plan, si, small) == aai.ERR_ARGUMENT
+    assert status_of(aai.run_device, plan, si, di, mode=4) == aai.ERR_ARGUMENT
+    assert status_of(aai.run_device, plan, si, di, arith=7) == aai.ERR_ARGUMENT
+    assert status_of(aai.run_device, plan, si, di, row0=3, row1=plan.dst_h + 1) == aai.ERR_ARGUMENT
+    assert status_of(aai.run_device_batch, plan, [], []) == aai.ERR_ARGUMENT
+    bad = aai.make_plan(64, 48, 1.0, -0.5, (32, 24), 10.0)   # the reference's second validation failure
+    assert bad.status == 2
+    assert status_of(aai.run_device, bad, si, di) == 2
+    assert status_of(aai.run_device_batch, bad, [si, si], [di, di]) == 2
+    # a source band that misses rows the canvas band needs is refused
+    part = aai.Image(si.data, si.pitch_bytes, si.width, si.height, 0, 8, si.dtype, si.channels)
+    assert status_of(aai.run_device, plan, part, di) == aai.ERR_ARGUMENT
+    assert "source rows" in aai.last_error()
