@@ -192,3 +192,23 @@ def test_run_entry_points_validate_before_touching_cuda(aai):
     part = aai.Image(si.data, si.pitch_bytes, si.width, si.height, 0, 8, si.dtype, si.channels)
     assert status_of(aai.run_device, plan, part, di) == aai.ERR_ARGUMENT
     assert "source rows" in aai.last_error()
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(aai, tmp_path):
+    """The drop-in boundary is a C ABI: include/aai.h compiles as pedantic C99 and a C program links the library."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "area_average_interpolation_b200")
+    src = tmp_path / "c_client.c"
+    src.write_text('#include <stdio.h>\n#include "aai.h"\n'
+                   "int main(void) {\n"
+                   "    aai_plan p;\n"
+                   "    int st = aai_plan_create(512, 512, 1, 1, 0.5, 0.5, 256, 256, 0.0, &p);\n"
+                   '    printf("%d %lld %lld %s|\\n", st, (long long)p.dst_w, (long long)p.dst_h, aai_status_string(1));\n'
+                   "    return st;\n}\n")
+    exe = str(tmp_path / "c_client")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"),
+                    str(src), "-L" + libdir, "-laai_b200", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    assert out.strip() == "0 256 256 Assumed X & Y resolution are same.|"
