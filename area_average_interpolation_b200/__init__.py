@@ -15,7 +15,7 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("AAI_B200_LIB") or os.path.join(_HERE, "libaai_b200.so")  # env override: developer builds only
+LIB_PATH = os.path.join(_HERE, "libaai_b200.so")  # (developer A/B tools assign another build here before lib() is called)
 
 AAI_OK = 0
 ERR_RESOLUTION_XY, ERR_RESOLUTION_NONPOS, ERR_NO_ROWS, ERR_NO_COLUMNS = 1, 2, 3, 4

@@ -169,6 +169,27 @@ AaiKernelParams aai_make_kernel_params(const aai_plan &p, const aai_image &src, 
     return k;
 }
 
+// One kernel of the path over canvas rows [kp.row0, kp.row1): rows sit on grid.y (<= 65535 CTAs), so very tall row
+// ranges (line scans, large upscales) are cut into several launches; bands are independent, the result is the same.
+static int launch_rows(const aai_plan &plan, int mode, int arith, AaiKernelParams kp, int src_dtype, int dst_dtype,
+                       void *stream) {
+    const int32_t row0 = kp.row0, row1 = kp.row1;
+    for (int64_t a = row0; a < row1; a += AAI_MAX_ROWS_PER_LAUNCH) {
+        kp.row0 = (int32_t)a;
+        kp.row1 = (int32_t)(a + AAI_MAX_ROWS_PER_LAUNCH < row1 ? a + AAI_MAX_ROWS_PER_LAUNCH : row1);
+        int e;
+        if (mode == AAI_MODE_FAST)
+            e = aai_launch_fast(kp, arith, src_dtype, dst_dtype, stream);
+        else if (plan.axis_aligned)
+            e = aai_launch_separable(kp, arith, src_dtype, dst_dtype, stream);
+        else
+            e = aai_launch_overlap(kp, arith, src_dtype, dst_dtype, stream);
+        if (e != (int)cudaSuccess) return e;
+        g_launches.fetch_add(1);
+    }
+    return (int)cudaSuccess;
+}
+
 extern "C" {
 
 const char *aai_last_error(void) { return g_error; }
@@ -235,9 +256,10 @@ static int copy_rows(const aai_image *dst, const aai_image *src, cudaMemcpyKind 
     const size_t row_bytes = (size_t)(band->width * band->channels) * elem_size(band->dtype);
     const char *s = (const char *)src->data + (kind == cudaMemcpyHostToDevice ? (band->y0 - src->y0) * src->pitch_bytes : 0);
     char *d = (char *)dst->data + (kind == cudaMemcpyDeviceToHost ? (band->y0 - dst->y0) * dst->pitch_bytes : 0);
-    if (dst->pitch_bytes == src->pitch_bytes)  // same pitch: one linear copy (faster DMA than a strided 2-D copy)
-        AAI_CUDA(cudaMemcpyAsync(d, s, (size_t)src->pitch_bytes * (size_t)(band->rows - 1) + row_bytes, kind,
-                                 (cudaStream_t)stream));
+    // Both images dense (no padding between rows): one linear copy (faster DMA than a strided 2-D copy).  With padded
+    // rows the copy must not touch the bytes between rows -- a host image may be a column view of a wider array.
+    if ((size_t)dst->pitch_bytes == row_bytes && (size_t)src->pitch_bytes == row_bytes)
+        AAI_CUDA(cudaMemcpyAsync(d, s, row_bytes * (size_t)band->rows, kind, (cudaStream_t)stream));
     else
         AAI_CUDA(cudaMemcpy2DAsync(d, (size_t)dst->pitch_bytes, s, (size_t)src->pitch_bytes, row_bytes,
                                    (size_t)band->rows, kind, (cudaStream_t)stream));
@@ -264,9 +286,8 @@ int aai_image_copy_rows(const aai_image *dst, const aai_image *src, int64_t y0, 
     const size_t row_bytes = (size_t)(src->width * src->channels) * elem_size(src->dtype);
     char *d = (char *)dst->data + (y0 - dst->y0) * dst->pitch_bytes;
     const char *s = (const char *)src->data + (y0 - src->y0) * src->pitch_bytes;
-    if ((size_t)dst->pitch_bytes == (size_t)src->pitch_bytes)  // same pitch: one linear copy (padding included)
-        AAI_CUDA(cudaMemcpyAsync(d, s, (size_t)src->pitch_bytes * (size_t)(y1 - y0), cudaMemcpyDefault,
-                                 (cudaStream_t)stream));
+    if ((size_t)dst->pitch_bytes == row_bytes && (size_t)src->pitch_bytes == row_bytes)  // dense: one linear copy
+        AAI_CUDA(cudaMemcpyAsync(d, s, row_bytes * (size_t)(y1 - y0), cudaMemcpyDefault, (cudaStream_t)stream));
     else
         AAI_CUDA(cudaMemcpy2DAsync(d, (size_t)dst->pitch_bytes, s, (size_t)src->pitch_bytes, row_bytes,
                                    (size_t)(y1 - y0), cudaMemcpyDefault, (cudaStream_t)stream));
@@ -334,15 +355,8 @@ int aai_run_device(const aai_plan *plan, int mode, int arith, const aai_image *s
     AAI_CUDA(cudaSetDevice(device));
     AaiKernelParams kp = aai_make_kernel_params(*plan, *src, *dst, row0, row1);
     kp.quirk = mode == AAI_MODE_AREA_AVERAGE_EXACT ? 0 : 1;
-    int e;
-    if (mode == AAI_MODE_FAST)
-        e = aai_launch_fast(kp, arith, src->dtype, dst->dtype, stream);
-    else if (plan->axis_aligned)
-        e = aai_launch_separable(kp, arith, src->dtype, dst->dtype, stream);
-    else
-        e = aai_launch_overlap(kp, arith, src->dtype, dst->dtype, stream);
+    const int e = launch_rows(*plan, mode, arith, kp, src->dtype, dst->dtype, stream);
     if (e != (int)cudaSuccess) return cuda_fail((cudaError_t)e, "kernel launch");
-    g_launches.fetch_add(1);
     return AAI_OK;
 }
 
@@ -472,15 +486,8 @@ int aai_run_device_batch(const aai_plan *plan, int mode, int arith, const aai_im
             kp.dst_batch_stride = dstride;
             kp.src_batch_rows = (int32_t)srows;
             kp.dst_batch_rows = (int32_t)drows;
-            int e;
-            if (mode == AAI_MODE_FAST)
-                e = aai_launch_fast(kp, arith, s0.dtype, d0.dtype, stream);
-            else if (plan->axis_aligned)
-                e = aai_launch_separable(kp, arith, s0.dtype, d0.dtype, stream);
-            else
-                e = aai_launch_overlap(kp, arith, s0.dtype, d0.dtype, stream);
+            const int e = launch_rows(*plan, mode, arith, kp, s0.dtype, d0.dtype, stream);
             if (e != (int)cudaSuccess) return cuda_fail((cudaError_t)e, "batched kernel launch");
-            g_launches.fetch_add(1);
         }
         return AAI_OK;
     }
@@ -533,7 +540,9 @@ int aai_run_host_band(const aai_plan *plan, int mode, int arith, const aai_image
     const int64_t band_rows = row1 - row0;
     int chunks = 1;
     if (total_bytes >= ((size_t)48 << 20) && band_rows >= 64) chunks = (int)(band_rows < 32 * 16 ? band_rows / 16 : 32);
+#ifdef AAI_DEV_KNOBS  // developer builds only; the shipped library reads no environment
     if (const char *e = getenv("AAI_HOST_CHUNKS")) chunks = atoi(e) > 0 ? atoi(e) : chunks;
+#endif
     if (chunks > band_rows) chunks = (int)band_rows;
     if (chunks <= 1) {
         AAI_CUDA(cudaEventRecord(w->ev[0], st));

@@ -12,12 +12,6 @@
 
 namespace aai_dev {
 
-#ifndef AAI_TILE_W
-#define AAI_TILE_W 16
-#endif
-#ifndef AAI_TILE_H
-#define AAI_TILE_H 8
-#endif
 // canvas pixels per CTA (one thread each); a warp covers 32/TILE_W rows.  16x8 (128 threads, 6-7 CTAs/SM for the FP32
 // kernel) measured 3.7 % faster than 16x16 on config 4: same warps per SM, finer-grained CTA turnover; 32x4 and 8x16
 // re-measured on the final kernel: 1.478 / 1.463 ms against 1.466 ms (profiles/r1_v17_ab_occupancy_tiles.txt).

@@ -8,6 +8,16 @@
 #include "../../include/aai.h"
 #include "aai_cell.cuh"
 
+// canvas pixels per CTA of the one-thread-per-pixel kernels (see aai_device.cuh); rows go on grid.y, which CUDA limits
+// to 65535 blocks, so the C ABI cuts taller row ranges into several launches
+#ifndef AAI_TILE_W
+#define AAI_TILE_W 16
+#endif
+#ifndef AAI_TILE_H
+#define AAI_TILE_H 8
+#endif
+#define AAI_MAX_ROWS_PER_LAUNCH (65535LL * AAI_TILE_H)
+
 // Everything a kernel needs, passed by value (__grid_constant__).  Built on the host in FP64 from the plan.
 struct AaiKernelParams {
     // canvas-pixel centre expression of Source.cpp:212-219

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H) fast_kernel_f32(const __grid_c
 template <typename T>
 __global__ void __launch_bounds__(256) expand_kernel(const __grid_constant__ AaiKernelParams kp) {
     const int mx = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int my = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int my = kp.row0 + blockIdx.y * 4 + (threadIdx.x >> 6);  // row0: first expanded row of this launch
     if (mx >= kp.mod_w || my >= kp.mod_h) return;
     int sx, sy;
     mod_to_src(kp, mx, my, sx, sy);
@@ -298,8 +298,11 @@ int aai_launch_overlap(const AaiKernelParams &kp, int arith, int src_dtype, int 
     // FP64 arithmetic: the unrolled kernel when the footprint fits its register arrays, else the rolled one
     // (its general-frame addressing divides by the scale with a multiply-high, exact below 2^32 / scale)
     const uint64_t max_e = (uint64_t)(kp.mod_w > kp.mod_h ? kp.mod_w : kp.mod_h);
-    if (kp.shape.sn > 0.0 && kp.shape.cs > 0.0 && max_e * (uint64_t)kp.scale < 0x100000000ULL &&
-        !getenv("AAI_F64_ROLLED")) {
+    bool unrolled = kp.shape.sn > 0.0 && kp.shape.cs > 0.0 && max_e * (uint64_t)kp.scale < 0x100000000ULL;
+#ifdef AAI_DEV_KNOBS  // developer builds only; the shipped library reads no environment
+    if (getenv("AAI_F64_ROLLED")) unrolled = false;
+#endif
+    if (unrolled) {
         const int n = (int)floor(2.0 * kp.hb + 1.0 + 2e-9) + 1;  // cells per axis within hb + 1/2 + 1e-9 of the centre
         int e = (int)cudaErrorNotSupported;
         if (n <= 4) e = aai_launch_overlap_f64_n4(kp, src_dtype, dst_dtype, stream);
@@ -323,15 +326,23 @@ int aai_launch_separable(const AaiKernelParams &kp, int arith, int src_dtype, in
 }
 int aai_launch_expand(const AaiKernelParams &kp, int elem_bytes, void *stream) {
     if (kp.mod_w <= 0 || kp.mod_h <= 0) return (int)cudaSuccess;
-    const dim3 grid((kp.mod_w + 63) / 64, (kp.mod_h + 3) / 4);
     cudaStream_t st = (cudaStream_t)stream;
-    switch (elem_bytes) {
-        case 1: expand_kernel<uint8_t><<<grid, 256, 0, st>>>(kp); break;
-        case 4: expand_kernel<float><<<grid, 256, 0, st>>>(kp); break;
-        case 8: expand_kernel<double><<<grid, 256, 0, st>>>(kp); break;
-        default: return (int)cudaErrorInvalidValue;
+    AaiKernelParams k = kp;
+    constexpr int kSlab = 65535 * 4;  // expanded rows per launch (grid.y limit)
+    for (int r0 = 0; r0 < kp.mod_h; r0 += kSlab) {
+        const int rows = kp.mod_h - r0 < kSlab ? kp.mod_h - r0 : kSlab;
+        const dim3 grid((kp.mod_w + 63) / 64, (rows + 3) / 4);
+        k.row0 = r0;
+        switch (elem_bytes) {
+            case 1: expand_kernel<uint8_t><<<grid, 256, 0, st>>>(k); break;
+            case 4: expand_kernel<float><<<grid, 256, 0, st>>>(k); break;
+            case 8: expand_kernel<double><<<grid, 256, 0, st>>>(k); break;
+            default: return (int)cudaErrorInvalidValue;
+        }
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
     }
-    return (int)cudaGetLastError();
+    return (int)cudaSuccess;
 }
 
 int aai_launch_fast(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream) {

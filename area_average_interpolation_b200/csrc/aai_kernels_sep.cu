@@ -20,6 +20,7 @@
 // TMA tile coordinates must be 16-byte aligned in the innermost dimension: the window origin is rounded down.
 #include <cuda.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 
@@ -323,21 +324,52 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// driver entry point, resolved once (thread-safe: aai_run_host drives one host thread per device)
 EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static const EncodeTiledFn fn = [] {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-        else
-            cudaGetLastError();
-    }
+            return (EncodeTiledFn)p;
+        cudaGetLastError();
+        return (EncodeTiledFn) nullptr;
+    }();
     return fn;
 }
+
+constexpr int kSepMaxDevices = 64;
+// SM count of the current device (cached per device; 0 = not yet queried)
+int sm_count_of(int dev) {
+    static std::atomic<int> cache[kSepMaxDevices];
+    if (dev < 0 || dev >= kSepMaxDevices) return 148;
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = 148;
+        }
+        cache[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
+// The encoded tensor map of the last launch of this thread, reused while the source view is the same (a cfg-1 sized
+// image is launch-latency bound: re-encoding the map and re-setting the kernel attribute was most of its host cost).
+struct TmapKey {
+    const void *src;
+    int64_t pitch, batch_stride;
+    int32_t w, rows, batch, bw, bh, dtype;
+    bool operator==(const TmapKey &o) const {
+        return src == o.src && pitch == o.pitch && batch_stride == o.batch_stride && w == o.w && rows == o.rows &&
+               batch == o.batch && bw == o.bw && bh == o.bh && dtype == o.dtype;
+    }
+};
+struct TmapCache {
+    bool valid = false;
+    TmapKey key;
+    CUtensorMap map;
+};
 
 template <typename TI>
 CUtensorMapDataType tmap_dtype();
@@ -358,8 +390,10 @@ cudaError_t launch_sep(const AaiKernelParams &kp, cudaStream_t stream) {
     SepParams sp;
     sp.tw = TW;
     sp.stages = 2;
-    if (const char *e = getenv("AAI_SEP_STAGES")) sp.stages = atoi(e);  // developer knobs (sweeps in profiles/)
+#ifdef AAI_DEV_KNOBS  // developer builds only (sweeps in profiles/); the shipped library reads no environment
+    if (const char *e = getenv("AAI_SEP_STAGES")) sp.stages = atoi(e);
     if (sp.stages < 2 || sp.stages > 8) return cudaErrorNotSupported;
+#endif
     const int batch = kp.batch > 0 ? kp.batch : 1;
     const int rows = kp.row1 - kp.row0;
     // tile height: the tallest of 48 / 32 / 16 canvas rows whose ring of source windows leaves room for two CTAs per SM
@@ -367,8 +401,10 @@ cudaError_t launch_sep(const AaiKernelParams &kp, cudaStream_t stream) {
     size_t tile_bytes = 0, wgt_bytes = 0, smem = 0;
     bool found = false;
     for (int th : {48, 32, 16}) {
+#ifdef AAI_DEV_KNOBS
         if (const char *e = getenv("AAI_SEP_TH")) th = atoi(e);
         if (th < 8 || th > 256 || th % (SEP_THREADS / TW) != 0) return cudaErrorNotSupported;
+#endif
         sp.th = th;
         // the window must hold MAXT taps starting at the first cell of the LAST column / row of the tile
         // (+ align-1 columns because the window origin is rounded down to a 16-byte boundary)
@@ -382,44 +418,57 @@ cudaError_t launch_sep(const AaiKernelParams &kp, cudaStream_t stream) {
             found = true;
             break;
         }
+#ifdef AAI_DEV_KNOBS
         if (getenv("AAI_SEP_TH")) break;
+#endif
     }
     if (!found && (sp.bw > 256 || sp.bh > 256 || sp.bw < MAXT || sp.bh < MAXT || smem > 220 * 1024))
         return cudaErrorNotSupported;
     sp.tiles_x = (kp.dst_w + TW - 1) / TW;
     sp.tiles_y = (rows + sp.th - 1) / sp.th;
     // strips are cut into segments so that the grid still fills the device (~4 CTAs per SM) when the batch is small
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (sm_count <= 0) sm_count = 148;
-    }
-    const int want_ctas = 4 * sm_count;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return cudaGetLastError();
+    const int want_ctas = 4 * sm_count_of(dev);
     int segs = (want_ctas + sp.tiles_x * batch - 1) / (sp.tiles_x * batch);
     segs = segs < 1 ? 1 : (segs > sp.tiles_y ? sp.tiles_y : segs);
     sp.tiles_per_cta = (sp.tiles_y + segs - 1) / segs;
     segs = (sp.tiles_y + sp.tiles_per_cta - 1) / sp.tiles_per_cta;
 
-    CUtensorMap tmap;
-    const cuuint64_t gdim[3] = {(cuuint64_t)kp.src_w, (cuuint64_t)kp.src_rows, (cuuint64_t)batch};
-    const cuuint64_t gstride[2] = {(cuuint64_t)kp.src_pitch,
-                                   (cuuint64_t)(batch > 1 ? kp.src_batch_stride : kp.src_pitch * (int64_t)kp.src_rows)};
-    const cuuint32_t box[3] = {(cuuint32_t)sp.bw, (cuuint32_t)sp.bh, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    if (gstride[1] % 16 != 0) return cudaErrorNotSupported;
-    const CUresult r = enc(&tmap, tmap_dtype<TI>(), 3, const_cast<void *>(kp.src), gdim, gstride, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return cudaErrorNotSupported;
+    const int64_t batch_stride = batch > 1 ? kp.src_batch_stride : kp.src_pitch * (int64_t)kp.src_rows;
+    if (batch_stride % 16 != 0) return cudaErrorNotSupported;
+    static thread_local TmapCache cache;  // per kernel instantiation and host thread
+    const TmapKey key = {kp.src, kp.src_pitch, batch_stride, kp.src_w, kp.src_rows, batch, sp.bw, sp.bh, (int32_t)tmap_dtype<TI>()};
+    if (!cache.valid || !(cache.key == key)) {
+        const cuuint64_t gdim[3] = {(cuuint64_t)kp.src_w, (cuuint64_t)kp.src_rows, (cuuint64_t)batch};
+        const cuuint64_t gstride[2] = {(cuuint64_t)kp.src_pitch, (cuuint64_t)batch_stride};
+        const cuuint32_t box[3] = {(cuuint32_t)sp.bw, (cuuint32_t)sp.bh, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = enc(&cache.map, tmap_dtype<TI>(), 3, const_cast<void *>(kp.src), gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            cache.valid = false;
+            return cudaErrorNotSupported;
+        }
+        cache.key = key;
+        cache.valid = true;
+    }
+    const CUtensorMap &tmap = cache.map;
+#ifdef AAI_DEV_KNOBS
     if (getenv("AAI_DEBUG"))
         fprintf(stderr, "[aai] separable TMA: TI=%d bytes TA=%d bytes TW=%d MAXT=%d box %dx%d tiles %dx%d smem %zu src %p pitch %lld "
                 "w %d rows %d\n", esz, (int)sizeof(TA), TW, MAXT, sp.bw, sp.bh, sp.tiles_x, sp.tiles_y, smem, kp.src,
                 (long long)kp.src_pitch, kp.src_w, kp.src_rows);
+#endif
     auto kernel = separable_tma_kernel<TI, TO, TA, TW, MAXT>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    // dynamic shared-memory limit of this instantiation: raised once per device (grow-only)
+    static std::atomic<int> smem_set[kSepMaxDevices];
+    if (dev < 0 || dev >= kSepMaxDevices || smem_set[dev].load(std::memory_order_relaxed) < (int)smem) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < kSepMaxDevices) smem_set[dev].store((int)smem, std::memory_order_relaxed);
+    }
     kernel<<<dim3(sp.tiles_x * segs, batch), SEP_BLOCK, smem, stream>>>(tmap, kp, sp);
     return cudaGetLastError();
 }

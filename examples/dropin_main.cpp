@@ -6,7 +6,7 @@
 
 #include "../area_average_interpolation_b200/csrc/aai.hpp"
 
-int main() {
+int main(int argc, char **argv) {
     using namespace aai_b200;
     IMG src(911, std::vector<double>(911));
     for (size_t y = 0; y < src.size(); ++y)
@@ -18,6 +18,12 @@ int main() {
     if (!ret.first) {
         std::printf("%s\nRun terminated abnormally.\n", ret.second.c_str());
         return -1;
+    }
+    if (argc > 1) {  // whole result as raw doubles, row-major (the parity test compares every pixel with the oracle)
+        std::FILE *f = std::fopen(argv[1], "wb");
+        if (!f) return -2;
+        for (const auto &row : dst) std::fwrite(row.data(), sizeof(double), row.size(), f);
+        std::fclose(f);
     }
     std::printf("dst %zux%zu, dstIsocenter (%g, %g), dst[79][79] = %.10g\nRun terminated correctly.\n",
                 dst.empty() ? 0 : dst.front().size(), dst.size(), dstIsocenter.first, dstIsocenter.second, dst[79][79]);

@@ -1,7 +1,7 @@
 // TEST-ONLY host build of the device cell arithmetic (csrc/aai_cell.cuh), so that the CPU suite can compare
 // the kernels' closed form with the oracle pair by pair without a GPU.  Never linked into the product.
 #include <cmath>
-#include "../area_average_interpolation_b200/csrc/aai_cell.cuh"
+#include "cell_legacy_forms.h"
 
 static AaiShape make_shape(double c, double s, double L) { return aai_make_shape(c, s, L); }
 

@@ -34,7 +34,8 @@ def test_dropin_matches_oracle_on_the_reference_user_settings(tmp_path, built):
     from oracle import port
 
     exe = _build(tmp_path, built)
-    out = subprocess.run([exe], capture_output=True, text=True)
+    dump = str(tmp_path / "dst.f64")
+    out = subprocess.run([exe, dump], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "Run terminated correctly." in out.stdout
     # same synthetic image as examples/dropin_main.cpp, the reference's shipped settings (Source.cpp:1528-1534)
@@ -45,3 +46,8 @@ def test_dropin_matches_oracle_on_the_reference_user_settings(tmp_path, built):
     assert f"dstIsocenter ({iso[0]:g}, {iso[1]:g})" in out.stdout
     got = float(out.stdout.split("dst[79][79] = ")[1].split()[0])
     assert abs(got - want[79, 79]) <= 1e-9 * abs(want[79, 79])
+    # the WHOLE image that the C++ mirror returned (flatten -> aai_run_host -> unflatten), against the oracle
+    whole = np.fromfile(dump, dtype=np.float64).reshape(want.shape)
+    err = np.abs(whole - want) / np.maximum(np.abs(want), 1e-300)
+    err[want == 0] = np.abs(whole[want == 0])
+    assert err.max() <= 1e-9, float(err.max())

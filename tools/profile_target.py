@@ -15,9 +15,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", type=int, default=4)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--arith", default="f64")
+ap.add_argument("--lib", default="", help="another build of libaai_b200.so (A/B variants)")
 ap.add_argument("--batch", type=int, default=0, help="config 5: slices per launch (aai_run_device_batch)")
 args = ap.parse_args()
 cfg = CONFIGS[args.config]
+if args.lib:
+    aai.LIB_PATH = args.lib
 dev = torch.device("cuda:0")
 plan = aai.make_plan(cfg["w"], cfg["h"], 1.0, cfg["ratio"], cfg["iso"], cfg["angle"])
 tail = (cfg["ch"],) if cfg["ch"] > 1 else ()
