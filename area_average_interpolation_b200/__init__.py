@@ -120,6 +120,26 @@ def lib() -> C.CDLL:
         L.aai_run_host_band.restype = C.c_int
         L.aai_run_host_band.argtypes = [C.POINTER(Plan), C.c_int, C.c_int, C.POINTER(Image), C.POINTER(Image),
                                         C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int]
+        L.aai_run_host_batch.restype = C.c_int
+        L.aai_run_host_batch.argtypes = [C.POINTER(Plan), C.c_int, C.c_int, C.POINTER(Image), C.POINTER(Image),
+                                         C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.aai_peer_create.restype = C.c_int
+        L.aai_peer_create.argtypes = [C.POINTER(Plan), C.c_int32, C.c_int32, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(C.c_void_p)]
+        L.aai_peer_export.restype = C.c_int
+        L.aai_peer_export.argtypes = [C.c_void_p, C.c_char_p]
+        L.aai_peer_connect.restype = C.c_int
+        L.aai_peer_connect.argtypes = [C.c_void_p, C.c_char_p]
+        L.aai_peer_owned_rows.restype = C.c_int
+        L.aai_peer_owned_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.aai_peer_band.restype = C.c_int
+        L.aai_peer_band.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.aai_peer_run.restype = C.c_int
+        L.aai_peer_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(Image), C.POINTER(Image), C.c_void_p, C.c_int]
+        L.aai_peer_device_source.restype = C.c_int
+        L.aai_peer_device_source.argtypes = [C.c_void_p, C.POINTER(Image)]
+        L.aai_peer_destroy.restype = C.c_int
+        L.aai_peer_destroy.argtypes = [C.c_void_p]
         L.aai_launch_count.restype = C.c_int64
         L.aai_last_host_timing.restype = C.c_int
         L.aai_last_host_timing.argtypes = [C.POINTER(C.c_float)] * 3
@@ -313,6 +333,67 @@ def run_host_band(plan: Plan, src_img: Image, dst_img: Image, row0: int, row1: i
                                    int(row0), int(row1), int(device), C.c_void_p(stream), int(bool(synchronize))))
 
 
+def run_host_batch(plan: Plan, src_imgs: Sequence[Image], dst_imgs: Sequence[Image], mode: int = MODE_AREA_AVERAGE,
+                   arith: int = ARITH_F64, device: int = 0, stream: int = 0, synchronize: bool = True) -> None:
+    """``aai_run_host_batch``: a batch of whole HOST images sharing one plan, pipelined through the batched kernels."""
+    n = len(src_imgs)
+    sa, da = (Image * n)(*src_imgs), (Image * n)(*dst_imgs)
+    _check(lib().aai_run_host_batch(C.byref(plan), int(mode), int(arith), sa, da, n, int(device), C.c_void_p(stream),
+                                    int(bool(synchronize))))
+
+
+PEER_BLOB_BYTES = 2048
+
+
+class PeerGroup:
+    """``aai_peer_*`` (include/aai.h): ONE large image over one process per GPU, end to end from host buffers -- every
+    source row crosses PCIe once, halos move over NVLink, no NCCL and no barrier per step.
+
+    ``all_gather(obj) -> list`` is the caller's out-of-band channel (e.g. ``torch.distributed.all_gather_object``), used
+    once to exchange the connection blobs."""
+
+    def __init__(self, plan: Plan, dtype: int, channels: int, rank: int, world: int, device: int, all_gather):
+        self.plan, self.rank, self.world, self.device = plan, rank, world, device
+        self._h = C.c_void_p()
+        _check(lib().aai_peer_create(C.byref(plan), int(dtype), int(channels), int(rank), int(world), int(device),
+                                     C.byref(self._h)))
+        try:
+            buf = C.create_string_buffer(PEER_BLOB_BYTES)
+            _check(lib().aai_peer_export(self._h, buf))
+            blobs = all_gather(buf.raw)
+            if len(blobs) != world or any(len(b) != PEER_BLOB_BYTES for b in blobs):
+                raise AaiError(ERR_ARGUMENT, "peer group: the gather must return one blob per rank, in rank order")
+            _check(lib().aai_peer_connect(self._h, b"".join(blobs)))
+        except Exception:
+            self.close()
+            raise
+
+    def owned_rows(self) -> Tuple[int, int]:
+        a, b = C.c_int64(), C.c_int64()
+        _check(lib().aai_peer_owned_rows(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def band(self) -> Tuple[int, int]:
+        a, b = C.c_int64(), C.c_int64()
+        _check(lib().aai_peer_band(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def device_source(self) -> Image:
+        img = Image()
+        _check(lib().aai_peer_device_source(self._h, C.byref(img)))
+        return img
+
+    def run(self, host_src: Image, host_dst: Image, mode: int = MODE_AREA_AVERAGE, arith: int = ARITH_F64,
+            stream: int = 0, synchronize: bool = True) -> None:
+        _check(lib().aai_peer_run(self._h, int(mode), int(arith), C.byref(host_src), C.byref(host_dst),
+                                  C.c_void_p(stream), int(bool(synchronize))))
+
+    def close(self) -> None:
+        if self._h:
+            lib().aai_peer_destroy(self._h)
+            self._h = C.c_void_p()
+
+
 @dataclass
 class Result:
     ok: bool
@@ -379,5 +460,5 @@ __all__ = [
     "AreaAverageInterpolation", "Result", "Plan", "Image", "AaiError", "make_plan", "partition_rows",
     "band_source_window", "covered_pixels", "device_count", "launch_count", "last_host_timing", "run_device", "run_device_batch", "expand_device", "measure_fp32_tflops", "image_alloc", "image_free", "image_upload", "image_download", "image_copy_rows",
     "ipc_export", "ipc_open", "ipc_close",
-    "run_host", "run_host_band", "tensor_image", "status_string", "last_error", "lib", "LIB_PATH",
+    "run_host", "run_host_band", "run_host_batch", "PeerGroup", "tensor_image", "status_string", "last_error", "lib", "LIB_PATH",
 ]

@@ -643,6 +643,96 @@ int aai_run_host_band(const aai_plan *plan, int mode, int arith, const aai_image
     return AAI_OK;
 }
 
+int aai_run_host_batch(const aai_plan *plan, int mode, int arith, const aai_image *srcs, const aai_image *dsts,
+                       int n_images, int device, void *stream, int synchronize) {
+    if (!plan || !srcs || !dsts || n_images <= 0) {
+        aai_set_error("aai_run_host_batch: bad argument");
+        return AAI_ERR_ARGUMENT;
+    }
+    for (int k = 0; k < n_images; ++k) {
+        const int r = check_host_images("aai_run_host_batch", plan, &srcs[k], &dsts[k], true);
+        if (r != AAI_OK) return r;
+        if (srcs[k].dtype != srcs[0].dtype || dsts[k].dtype != dsts[0].dtype || srcs[k].channels != srcs[0].channels) {
+            aai_set_error("aai_run_host_batch: the images of a batch must share element types and channel count");
+            return AAI_ERR_ARGUMENT;
+        }
+    }
+    if (aai_device_count() <= device || device < 0) {
+        aai_set_error("aai_run_host_batch: device %d not present; this library has no CPU fallback", device);
+        return aai_device_count() <= 0 ? AAI_ERR_NO_DEVICE : AAI_ERR_ARGUMENT;
+    }
+    // Ring of kRing groups of `per` slices each in the device workspace: group i is uploaded (one copy per slice),
+    // resampled with ONE batched launch and downloaded, on three streams; its buffers are reused by group i + kRing
+    // once its kernel (source buffers) resp. its download (canvas buffers) has finished.
+    constexpr int kRing = 3;
+    aai_image ds = srcs[0], dd = dsts[0];
+    ds.pitch_bytes = round_up(ds.width * ds.channels * (int64_t)elem_size(ds.dtype), 512);
+    dd.pitch_bytes = round_up(dd.width * dd.channels * (int64_t)elem_size(dd.dtype), 512);
+    const size_t s_bytes = (size_t)ds.pitch_bytes * (size_t)ds.height, d_bytes = (size_t)dd.pitch_bytes * (size_t)dd.height;
+    int per = (int)(((size_t)192 << 20) / (s_bytes + d_bytes));
+    per = per < 1 ? 1 : (per > 16 ? 16 : per);
+    if (per > n_images) per = n_images;
+    const int groups = (n_images + per - 1) / per;
+    std::lock_guard<std::mutex> busy(g_ws[device < kMaxDevices ? device : 0].busy);
+    Workspace *w = nullptr;
+    int r = workspace_get(device, s_bytes * (size_t)per * kRing, d_bytes * (size_t)per * kRing, &w);
+    if (r != AAI_OK) return r;
+    cudaStream_t st = stream ? (cudaStream_t)stream : w->stream;
+    if (w->done_valid) AAI_CUDA(cudaStreamWaitEvent(st, w->done, 0));
+    while ((int)w->chunk_ev.size() < 3 * kRing) {
+        cudaEvent_t e;
+        AAI_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        w->chunk_ev.push_back(e);
+    }
+    AAI_CUDA(cudaEventRecord(w->ev[0], st));
+    AAI_CUDA(cudaStreamWaitEvent(w->up, w->ev[0], 0));
+    AAI_CUDA(cudaStreamWaitEvent(w->dn, w->ev[0], 0));
+    std::vector<aai_image> gs((size_t)per), gd((size_t)per);
+    for (int g = 0; g < groups; ++g) {
+        const int slot = g % kRing, first = g * per, n = n_images - first < per ? n_images - first : per;
+        cudaEvent_t up_done = w->chunk_ev[3 * slot], k_done = w->chunk_ev[3 * slot + 1], dn_done = w->chunk_ev[3 * slot + 2];
+        if (g >= kRing) {  // the slot's previous occupant: its kernel has read the sources, its download the canvases
+            AAI_CUDA(cudaStreamWaitEvent(w->up, k_done, 0));
+            AAI_CUDA(cudaStreamWaitEvent(st, dn_done, 0));
+        }
+        for (int k = 0; k < n; ++k) {
+            gs[(size_t)k] = ds;
+            gs[(size_t)k].data = (char *)w->ptr[0] + ((size_t)slot * per + k) * s_bytes;
+            gd[(size_t)k] = dd;
+            gd[(size_t)k].data = (char *)w->ptr[1] + ((size_t)slot * per + k) * d_bytes;
+            r = aai_image_upload(&gs[(size_t)k], &srcs[first + k], device, w->up);
+            if (r != AAI_OK) return r;
+        }
+        AAI_CUDA(cudaEventRecord(up_done, w->up));
+        AAI_CUDA(cudaStreamWaitEvent(st, up_done, 0));
+        r = aai_run_device_batch(plan, mode, arith, gs.data(), gd.data(), n, device, st);
+        if (r != AAI_OK) return r;
+        AAI_CUDA(cudaEventRecord(k_done, st));
+        AAI_CUDA(cudaStreamWaitEvent(w->dn, k_done, 0));
+        for (int k = 0; k < n; ++k) {
+            r = aai_image_download(&dsts[first + k], &gd[(size_t)k], device, w->dn);
+            if (r != AAI_OK) return r;
+        }
+        AAI_CUDA(cudaEventRecord(dn_done, w->dn));
+    }
+    AAI_CUDA(cudaEventRecord(w->join_up, w->up));
+    AAI_CUDA(cudaEventRecord(w->join_dn, w->dn));
+    AAI_CUDA(cudaStreamWaitEvent(st, w->join_up, 0));
+    AAI_CUDA(cudaStreamWaitEvent(st, w->join_dn, 0));
+    AAI_CUDA(cudaEventRecord(w->ev[3], st));
+    AAI_CUDA(cudaEventRecord(w->done, st));
+    w->done_valid = true;
+    if (synchronize || !stream) {
+        AAI_CUDA(cudaStreamSynchronize(st));
+        float total = 0.f;
+        AAI_CUDA(cudaEventElapsedTime(&total, w->ev[0], w->ev[3]));
+        g_h2d_ms = total;
+        g_kernel_ms = 0.f;
+        g_d2h_ms = 0.f;
+    }
+    return AAI_OK;
+}
+
 int aai_run_host(const aai_plan *plan, int mode, int arith, const aai_image *src, const aai_image *dst,
                  const int *devices, int n_devices) {
     int rc = check_host_images("aai_run_host", plan, src, dst, true);

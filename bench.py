@@ -1,19 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the area-average interpolation hot path (BASELINE.json metric: output Mpixels/s, device-timed).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 4] [--impl ours|reference] [--no-extra]
 
 A "step" is one pass of the hot path over the whole workload (default: BASELINE config 4, the 16384x16384
 float32 slice, 0.37x, 17.3 deg -> 7591x7591 canvas).  With N > 1 (torchrun, one process per GPU) the canvas is
-split into row bands balanced by covered pixels; every rank holds its source halo + its band; there is no
+split into row bands balanced by kernel cost; every rank holds its source halo + its band; there is no
 data-path collective (bands are independent) -- only the barrier and the max-over-ranks of the timing.
 
 value     = canvas Mpixels/s with the source resident in HBM, CUDA events around exactly K steps (max over ranks)
-e2e       = the same metric through the host-buffer C-ABI call (aai_run_host_band): pinned host source ->
-            device, kernel, device -> pinned host canvas, all inside the timed region
-roofline  = the dominant kernel against its bound (FP32 pipe for the rotated clip path, HBM for the separable path)
+e2e       = the same metric through the host-buffer C-ABI call: pinned host source -> device, kernel, device ->
+            pinned host canvas, all inside the timed region (N = 1: aai_run_host_band, chunk-pipelined; N > 1: the
+            peer group of include/aai.h -- every source row crosses PCIe once, halos move over NVLink)
+roofline  = the dominant kernel against its bound (FP32 pipe for the rotated clip path, HBM for the separable path);
+            peak = the nominal FP32 rate (SMs x 128 lanes x 2 x max clock) resp. the measured HBM copy rate
 cpu_baseline = the reference's own CPU implementation (compiled upstream Source.cpp, 1 thread as shipped) on a
             bounded replica of the workload, timed on this box (rank 0, N = 1)
+verified  = after the timed regions: the canvas the end-to-end path produced is (a) bitwise equal to the band computed
+            from a source generated directly in HBM (independent of the upload / NVLink exchange) and (b) within
+            tolerance of the CPU oracle on the first and last row of every rank's band
+configs   = the other BASELINE shapes (cfg 1, 2, 3, 5), the FP64 kernel and fast mode on the headline shape, measured
+            the same way in the same run outside the headline's timed regions (all ranks take part under torchrun)
 
 --impl reference times the upstream CPU implementation on all host cores (one process per core, one replica image
 each per step).
@@ -92,6 +99,19 @@ def cpu_kind():
         return "reference"
     port.lib()
     return "port"
+
+
+def _verify_rows(src_rows, src_y0, cfg, mode, rows, channel):
+    """Checker leg (outside every timed region): the CPU oracle on canvas rows [rows[0], rows[1]) of the workload.
+    `src_rows` holds source rows [src_y0, src_y0 + len) -- everything those canvas rows can touch; the rest of the image
+    is never read (untouched virtual memory)."""
+    from oracle import port
+
+    full = np.empty((cfg["h"], cfg["w"]) + src_rows.shape[2:], dtype=src_rows.dtype)
+    full[src_y0:src_y0 + src_rows.shape[0]] = src_rows
+    st, want, _ = port.run(full, 1.0, cfg["ratio"], cfg["iso"], cfg["angle"], mode=mode, rows=rows, channel=channel)
+    assert st == 0
+    return want
 
 
 def reference_arm(args, cfg):
@@ -215,315 +235,440 @@ def bind_to_gpu_numa_node(torch, local):
     return None
 
 
-def our_arm(args, cfg):
-    import torch
-    import torch.distributed as dist
+class Bench:
+    """State shared by the measurements of one process (one rank)."""
 
-    import area_average_interpolation_b200 as aai
-    from area_average_interpolation_b200.sharding import band_for_rank, batch_slice
-    from area_average_interpolation_b200.synthetic import synthetic_image
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
+        import area_average_interpolation_b200 as aai
+
+        self.torch, self.dist, self.aai, self.args = torch, dist, aai, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one process per GPU)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.numa = bind_to_gpu_numa_node(torch, self.local) if self.world > 1 else None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = torch.cuda.current_stream().cuda_stream
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        self.hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        self.hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        self.sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+        self.n_sm = torch.cuda.get_device_properties(self.local).multi_processor_count
+        self.fp32_nominal = self.n_sm * 128 * 2 * self.sm_max * 1e6 / 1e12
+        self.fp64_nominal = self.n_sm * 64 * 2 * self.sm_max * 1e6 / 1e12
+        self.fp32_probe = None
+        try:
+            self.uuid = "GPU-" + str(torch.cuda.get_device_properties(self.local).uuid)
+        except Exception:
+            self.uuid = None
+        try:
+            self.latest = json.load(open(os.path.join(ROOT, "profiles", "latest.json")))
+        except Exception:
+            self.latest = {}
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # -- collectives used for TIMING / bookkeeping only (no data-path collective) ------------------------------------
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if world == 1:
+    def _reduce(self, x, op):
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=op)
         return t.item()
 
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return t.item()
+    def max_over_ranks(self, x):
+        return self._reduce(x, self.dist.ReduceOp.MAX)
 
-    if args.arith == "auto":
-        arith = aai.ARITH_F64 if cfg["dtype"] == "float64" else aai.ARITH_F32
-    else:
-        arith = aai.ARITH_F32 if args.arith == "f32" else aai.ARITH_F64
-    np_dt = np.dtype(cfg["dtype"])
-    t_dt = {"uint8": torch.uint8, "float32": torch.float32, "float64": torch.float64}[cfg["dtype"]]
-    out_dt = torch.float64 if cfg["dtype"] == "float64" else torch.float32
-    W, H, CH = cfg["w"], cfg["h"], cfg["ch"]
-    plan = aai.make_plan(W, H, 1.0, cfg["ratio"], cfg["iso"], cfg["angle"])
-    assert plan.status == 0, plan.message
-    seed = 20201 + args.config
-    stream = torch.cuda.current_stream().cuda_stream
-    shape_tail = (CH,) if CH > 1 else ()
+    def min_over_ranks(self, x):
+        return self._reduce(x, self.dist.ReduceOp.MIN)
 
-    peer = None
-    if cfg["batch"] == 1:
-        # one image, canvas row bands
-        band = band_for_rank(plan, rank, world)
-        host_dst = torch.empty((band.rows, plan.dst_w) + shape_tail, dtype=out_dt, pin_memory=True)
-        dev_dst = torch.empty((band.rows, plan.dst_w) + shape_tail, dtype=out_dt, device=dev)
-        di = aai.tensor_image(dev_dst, y0=band.row0, height=plan.dst_h)
-        hdi = aai.tensor_image(host_dst, y0=band.row0, height=plan.dst_h)
-        my_pixels = band.rows * plan.dst_w
-        launches_per_step = 1
-        d2h = band.rows * plan.dst_w * CH * host_dst.element_size()
-        if world > 1 and not args.no_peer:
-            # every source row crosses PCIe once (its owner uploads it); halos are pulled over NVLink (CUDA IPC)
+    def sum_over_ranks(self, x):
+        return self._reduce(x, self.dist.ReduceOp.SUM)
+
+    def gather(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def probe_fp32(self):
+        if self.fp32_probe is None:
             try:
-                from area_average_interpolation_b200.sharding import PeerSource
+                self.fp32_probe = self.aai.measure_fp32_tflops(self.local)
+            except Exception as exc:
+                print(f"[bench] FP32 probe failed: {exc}", file=sys.stderr)
+                self.fp32_probe = 0.0
+        return self.fp32_probe
 
-                def gather(obj):
-                    out = [None] * world
-                    dist.all_gather_object(out, obj)
-                    return out
+    # -- one workload ----------------------------------------------------------------------------------------------------
+    def measure(self, cfg_id, arith_name="auto", mode=1, steps=None, with_e2e=True, with_verify=True,
+                with_clocks=True, tag=None):
+        """Device-timed value, end-to-end value, roofline and verification of one BASELINE shape."""
+        torch, aai, args = self.torch, self.aai, self.args
+        from area_average_interpolation_b200.sharding import band_for_rank, batch_slice
+        from area_average_interpolation_b200.synthetic import synthetic_image_torch
 
-                peer = PeerSource(plan, aai._NP_TO_AAI[np_dt], CH, rank, world, local, band, gather)
-            except Exception as exc:  # IPC unavailable: every rank uploads its own halo from the host
-                print(f"[bench] rank {rank}: peer source exchange unavailable ({exc}); uploading halos from host",
-                      file=sys.stderr)
-                peer = None
-            ok = torch.tensor([1 if peer is not None else 0], device=dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if ok.item() == 0 and peer is not None:
-                peer.close()
-                peer = None
-        if peer is not None:
-            o0, o1 = peer.owned_rows()
-            host_src = torch.empty((o1 - o0, W) + shape_tail, dtype=t_dt, pin_memory=True)
-            synthetic_image(W, H, np_dt, seed, channels=CH, y0=o0, rows=o1 - o0, out=host_src.numpy())
-            hsi = aai.tensor_image(host_src, y0=o0, height=H)
-            si = peer.full
-            resident_bytes = (band.src_y1 - band.src_y0) * W * CH * np_dt.itemsize
-
-            def sync():
-                torch.cuda.current_stream().synchronize()
-                dist.barrier()
-
-            phases = os.environ.get("AAI_BENCH_PHASES")
-
-            def e2e_step():
-                t = [time.perf_counter()]
-                peer.upload_owned(hsi, stream)
-                if phases:
-                    torch.cuda.current_stream().synchronize(); t.append(time.perf_counter())
-                sync()                      # every owner's rows are on its device
-                if phases:
-                    t.append(time.perf_counter())
-                moved = peer.pull_halo(stream)      # NVLink peer copies of the rows this band needs but does not own
-                if phases:
-                    torch.cuda.current_stream().synchronize(); t.append(time.perf_counter())
-                aai.run_device(plan, si, di, band.row0, band.row1, arith=arith, device=local, stream=stream)
-                aai.image_download(hdi, di, local, stream)
-                if phases:
-                    torch.cuda.current_stream().synchronize(); t.append(time.perf_counter())
-                sync()                      # peers have finished reading before the next upload overwrites
-                if phases:
-                    t.append(time.perf_counter())
-                    print(f"[phases] rank {rank}: upload {1e3*(t[1]-t[0]):.2f} barrier {1e3*(t[2]-t[1]):.2f} pull "
-                          f"{1e3*(t[3]-t[2]):.2f} ({moved/1e6:.0f} MB) kernel+d2h {1e3*(t[4]-t[3]):.2f} barrier "
-                          f"{1e3*(t[5]-t[4]):.2f} ms", file=sys.stderr)
-
-            e2e_step()  # populates this rank's halo for the device-timed loop
-            h2d = (o1 - o0) * W * CH * np_dt.itemsize
+        cfg = CONFIGS[cfg_id]
+        steps = steps or args.steps
+        warm = max(args.warmup, 3)
+        rank, world, local, dev, stream = self.rank, self.world, self.local, self.dev, self.stream
+        if arith_name == "auto":
+            arith = aai.ARITH_F64 if cfg["dtype"] == "float64" else aai.ARITH_F32
         else:
+            arith = aai.ARITH_F32 if arith_name == "f32" else aai.ARITH_F64
+        np_dt = np.dtype(cfg["dtype"])
+        t_dt = {"uint8": torch.uint8, "float32": torch.float32, "float64": torch.float64}[cfg["dtype"]]
+        out_dt = t_dt  # the canvas has the image's own element type (8-bit in -> 8-bit out, round half up)
+        W, H, CH = cfg["w"], cfg["h"], cfg["ch"]
+        plan = aai.make_plan(W, H, 1.0, cfg["ratio"], cfg["iso"], cfg["angle"])
+        assert plan.status == 0, plan.message
+        seed = 20201 + cfg_id
+        tail = (CH,) if CH > 1 else ()
+        esz, osz = np_dt.itemsize, torch.empty((), dtype=out_dt).element_size()
+        kw = dict(mode=mode, arith=arith, device=local, stream=stream)
+        peer = None
+        info = {}
+
+        if cfg["batch"] == 1:
+            band = band_for_rank(plan, rank, world)
             halo_rows = band.src_y1 - band.src_y0
-            host_src = torch.empty((max(halo_rows, 1), W) + shape_tail, dtype=t_dt, pin_memory=True)
-            if halo_rows:
-                synthetic_image(W, H, np_dt, seed, channels=CH, y0=band.src_y0, rows=halo_rows,
-                                out=host_src.numpy()[:halo_rows])
-            dev_src = host_src.to(dev)
+            # this rank's source halo, generated directly in HBM (bit-identical to the host generator)
+            dev_src = synthetic_image_torch(W, H, np_dt, seed, channels=CH, y0=band.src_y0, rows=max(halo_rows, 1),
+                                            device=dev)
             si = aai.tensor_image(dev_src[:halo_rows] if halo_rows else dev_src, y0=band.src_y0, height=H)
-            hsi = aai.tensor_image(host_src[:halo_rows] if halo_rows else host_src, y0=band.src_y0, height=H)
-            resident_bytes = dev_src.numel() * dev_src.element_size()
+            dev_dst = torch.empty((band.rows, plan.dst_w) + tail, dtype=out_dt, device=dev)
+            di = aai.tensor_image(dev_dst, y0=band.row0, height=plan.dst_h)
+            my_pixels = band.rows * plan.dst_w
+            resident = dev_src.numel() * esz
 
-            def e2e_step():
-                aai.run_host_band(plan, hsi, hdi, band.row0, band.row1, arith=arith, device=local, stream=stream,
-                                  synchronize=False)
+            def step():
+                aai.run_device(plan, si, di, band.row0, band.row1, **kw)
 
-            h2d = halo_rows * W * CH * np_dt.itemsize
-
-        def step():
-            aai.run_device(plan, si, di, band.row0, band.row1, arith=arith, device=local, stream=stream)
-
-    else:
-        # batch of independent images: whole images per rank
-        lo, hi = batch_slice(cfg["batch"], rank, world)
-        n_img = hi - lo
-        distinct = min(n_img, 4)  # the host keeps a few distinct synthetic slices; the device batch is resident
-        host_src = torch.empty((distinct, H, W), dtype=t_dt, pin_memory=True)
-        for k in range(distinct):
-            synthetic_image(W, H, np_dt, seed + 1000 * (lo + k), out=host_src.numpy()[k])
-        host_dst = torch.empty((distinct, plan.dst_h, plan.dst_w), dtype=out_dt, pin_memory=True)
-        dev_src = torch.empty((n_img, H, W), dtype=t_dt, device=dev)
-        for k in range(n_img):
-            dev_src[k].copy_(host_src[k % distinct], non_blocking=True)
-        dev_dst = torch.empty((n_img, plan.dst_h, plan.dst_w), dtype=out_dt, device=dev)
-        sis = [aai.tensor_image(dev_src[k]) for k in range(n_img)]
-        dis = [aai.tensor_image(dev_dst[k]) for k in range(n_img)]
-        hsis = [aai.tensor_image(host_src[k]) for k in range(distinct)]
-        hdis = [aai.tensor_image(host_dst[k]) for k in range(distinct)]
-        my_pixels = n_img * plan.dst_w * plan.dst_h
-        launches_per_step = 1  # the equally strided batch is one launch (rank-3 TMA tensor map)
-
-        def step():
-            aai.run_device_batch(plan, sis, dis, arith=arith, device=local, stream=stream)
-
-        def e2e_step():
+        else:
+            band = None
+            lo, hi = batch_slice(cfg["batch"], rank, world)
+            n_img = hi - lo
+            distinct = min(n_img, 4)  # a few distinct synthetic slices; the device batch is resident
+            base = [synthetic_image_torch(W, H, np_dt, seed + 1000 * (lo + k), device=dev) for k in range(distinct)]
+            dev_src = torch.empty((n_img, H, W), dtype=t_dt, device=dev)
             for k in range(n_img):
-                aai.run_host_band(plan, hsis[k % distinct], hdis[k % distinct], 0, plan.dst_h, arith=arith,
-                                  device=local, stream=stream, synchronize=False)
+                dev_src[k].copy_(base[k % distinct])
+            dev_dst = torch.empty((n_img, plan.dst_h, plan.dst_w), dtype=out_dt, device=dev)
+            sis = [aai.tensor_image(dev_src[k]) for k in range(n_img)]
+            dis = [aai.tensor_image(dev_dst[k]) for k in range(n_img)]
+            my_pixels = n_img * plan.dst_w * plan.dst_h
+            resident = dev_src.numel() * esz
 
-        h2d = n_img * H * W * np_dt.itemsize
-        d2h = n_img * plan.dst_w * plan.dst_h * host_dst.element_size()
-        resident_bytes = dev_src.numel() * dev_src.element_size()
-        band = None
+            def step():
+                aai.run_device_batch(plan, sis, dis, **kw)
 
-    total_pixels = sum_over_ranks(float(my_pixels))
+        total_pixels = self.sum_over_ranks(float(my_pixels))
 
-    # ---- device-timed region -------------------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    uuid = None
-    try:
-        uuid = "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
-    except Exception:
-        pass
-    sampler = ClockSampler(uuid if rank == 0 else None)
-    if rank == 0:
-        sampler.start()
-    # untimed pre-load so that the clock sampler sees the loaded state even when K steps are only milliseconds
-    t_pre = time.perf_counter()
-    while time.perf_counter() - t_pre < 0.6:
-        step()
+        # ---- device-timed region -------------------------------------------------------------------------------------
+        for _ in range(warm):
+            step()
         torch.cuda.synchronize()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    before = aai.launch_count()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    launches = aai.launch_count() - before
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    ms_step = ms_total / args.steps
-    value = total_pixels / (ms_step * 1e-3) / 1e6
+        sampler = ClockSampler(self.uuid) if (rank == 0 and with_clocks) else None
+        if sampler:
+            sampler.start()
+        # untimed pre-load so that the clock sampler sees the loaded state even when K steps are only milliseconds
+        t_pre = time.perf_counter()
+        while time.perf_counter() - t_pre < (0.6 if with_clocks else 0.05):
+            step()
+            torch.cuda.synchronize()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        before = aai.launch_count()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        self.barrier()
+        launches = aai.launch_count() - before
+        ms_step = self.max_over_ranks(e0.elapsed_time(e1)) / steps
+        value = total_pixels / (ms_step * 1e-3) / 1e6
+        band_ms = self.gather(e0.elapsed_time(e1) / steps)
 
-    # ---- end-to-end region (host buffers through the C ABI) --------------------------------------------------
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e3.record()
-    barrier()
-    e2e_ms = max_over_ranks(e2.elapsed_time(e3)) / args.steps
-    clocks = sampler.stop() if rank == 0 else {}
-    h2d_total, d2h_total = sum_over_ranks(float(h2d)), sum_over_ranks(float(d2h))
+        # ---- end-to-end region (host buffers through the C ABI) --------------------------------------------------
+        e2e = None
+        host_dst = None
+        if with_e2e:
+            if cfg["batch"] == 1:
+                host_dst = torch.empty((band.rows, plan.dst_w) + tail, dtype=out_dt, pin_memory=True)
+                hdi = aai.tensor_image(host_dst, y0=band.row0, height=plan.dst_h)
+                d2h = band.rows * plan.dst_w * CH * osz
+                if world > 1 and not args.no_peer:
+                    try:
+                        peer = aai.PeerGroup(plan, aai._NP_TO_AAI[np_dt], CH, rank, world, local, self.gather)
+                    except Exception as exc:  # IPC unavailable: every rank uploads its own halo from the host
+                        print(f"[bench] rank {rank}: peer group unavailable ({exc}); uploading halos from host",
+                              file=sys.stderr)
+                        peer = None
+                    if self.min_over_ranks(1.0 if peer is not None else 0.0) == 0.0 and peer is not None:
+                        peer.close()
+                        peer = None
+                if peer is not None:
+                    o0, o1 = peer.owned_rows()
+                    host_src = torch.empty((max(o1 - o0, 1), W) + tail, dtype=t_dt, pin_memory=True)
+                    if o1 > o0:
+                        host_src[:o1 - o0].copy_(synthetic_image_torch(W, H, np_dt, seed, channels=CH, y0=o0,
+                                                                       rows=o1 - o0, device=dev))
+                    hsi = aai.tensor_image(host_src[:o1 - o0], y0=o0, height=H)
+                    h2d = (o1 - o0) * W * CH * esz
 
-    # ---- roofline of the dominant kernel ------------------------------------------------------------------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
-    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
-    if cfg["batch"] == 1:
-        nz = (dev_dst if CH == 1 else dev_dst[..., 0]) != 0
-        covered = sum_over_ranks(float(nz.sum().item()))
-    else:
-        covered = total_pixels
-    alg_bytes = (W * H * CH * np_dt.itemsize + plan.dst_w * plan.dst_h * CH * host_dst.element_size()) * cfg["batch"]
-    kernel_ms = ms_step
-    if plan.axis_aligned:
-        per_launch = alg_bytes / world
-        achieved = per_launch / (kernel_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "peak_source": hbm_src,
-                    "algorithmic": "each source byte read once + each canvas byte written once (SURVEY 8d)"}
-    else:
-        F = flops_per_covered_pixel(plan.side, plan.cos_t, plan.sin_t, CH)
-        nominal = n_sm * 128 * 2 * sm_max * 1e6 / 1e12
-        try:  # measured on this device right now (register-only FFMA probe in the library)
-            measured = aai.measure_fp32_tflops(local)
-        except Exception as exc:
-            print(f"[bench] FP32 probe failed: {exc}", file=sys.stderr)
-            measured = 0.0
-        fp32_peak = measured if 0.5 * nominal < measured < 1.1 * nominal else nominal
-        achieved = F * covered / world / (kernel_ms * 1e-3) / 1e12
-        roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                    "frac": achieved / fp32_peak, "traffic": None,
-                    "peak_source": (f"measured on this device by the library's FFMA probe ({measured:.2f} TFLOP/s; nominal "
-                                    f"{n_sm} SMs x 128 lanes x 2 x {sm_max:.0f} MHz = {nominal:.2f}; MEASURED_PEAKS.json "
-                                    "holds no FP32 figure)" if fp32_peak == measured else
-                                    f"nominal {n_sm} SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (FFMA probe unavailable; "
-                                    "MEASURED_PEAKS.json holds no FP32 figure)"),
-                    "peak_nominal": nominal,
-                    "algorithmic": f"{F:.0f} flop per covered canvas pixel x {covered / world:.0f} covered pixels per "
-                                   "launch (SURVEY 8d contract figure)",
-                    "hbm": {"achieved": alg_bytes / world / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                            "peak_source": hbm_src}}
-    try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "latest.json"))).get(f"cfg{args.config}", {})
+                    def e2e_step():
+                        peer.run(hsi, hdi, mode=mode, arith=arith, stream=stream, synchronize=False)
+
+                    info["e2e_source"] = ("peer group (include/aai.h): every source row uploaded once by its owner rank in "
+                                          "chunks, halos pulled over NVLink as the chunks land (CUDA IPC peer copies, device-"
+                                          "side flags), kernel + download chunk-pipelined; no NCCL and no host barrier per step")
+                else:
+                    host_src = torch.empty((max(halo_rows, 1), W) + tail, dtype=t_dt, pin_memory=True)
+                    host_src.copy_(dev_src)
+                    hsi = aai.tensor_image(host_src[:halo_rows] if halo_rows else host_src, y0=band.src_y0, height=H)
+                    h2d = halo_rows * W * CH * esz
+
+                    def e2e_step():
+                        aai.run_host_band(plan, hsi, hdi, band.row0, band.row1, mode=mode, arith=arith, device=local,
+                                          stream=stream, synchronize=False)
+
+                    info["e2e_source"] = "each rank uploads its band's source halo from pinned host memory (chunk-pipelined)"
+            else:
+                host_src = torch.empty((distinct, H, W), dtype=t_dt, pin_memory=True)
+                for k in range(distinct):
+                    host_src[k].copy_(base[k])
+                host_dst = torch.empty((distinct, plan.dst_h, plan.dst_w), dtype=out_dt, pin_memory=True)
+                hs_list = [aai.tensor_image(host_src[k % distinct]) for k in range(n_img)]
+                hd_list = [aai.tensor_image(host_dst[k % distinct]) for k in range(n_img)]
+                h2d = n_img * H * W * esz
+                d2h = n_img * plan.dst_w * plan.dst_h * osz
+
+                def e2e_step():
+                    aai.run_host_batch(plan, hs_list, hd_list, mode=mode, arith=arith, device=local, stream=stream,
+                                       synchronize=False)
+
+                info["e2e_source"] = ("aai_run_host_batch: slices uploaded, resampled (batched launches) and downloaded in "
+                                      "a 3-stream pipeline; the host keeps 4 distinct slices")
+            for _ in range(2):
+                e2e_step()
+            self.barrier()
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e2.record()
+            for _ in range(steps):
+                e2e_step()
+            e3.record()
+            self.barrier()
+            e2e_ms = self.max_over_ranks(e2.elapsed_time(e3)) / steps
+            e2e = {"value": total_pixels / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
+                   "h2d_bytes_per_step": self.sum_over_ranks(float(h2d)),
+                   "d2h_bytes_per_step": self.sum_over_ranks(float(d2h)), "ms_per_step": e2e_ms}
+        clocks = sampler.stop() if sampler else {}
+
+        # ---- verification (outside the timed regions) ----------------------------------------------------------------
+        verify = None
+        if with_verify:
+            verify = self._verify(cfg, cfg_id, plan, mode, arith, band, dev_dst, host_dst, step, seed,
+                                  lo if band is None else 0)
+
+        # ---- roofline of the dominant kernel ------------------------------------------------------------------------
+        if cfg["batch"] == 1:
+            # covered = canvas pixels whose footprint box meets the image (what the kernels evaluate; plan geometry)
+            covered = self.sum_over_ranks(float(aai.covered_pixels(plan, band.row0, band.row1)))
+        else:
+            covered = total_pixels
+        alg_bytes = (W * H * CH * esz + plan.dst_w * plan.dst_h * CH * osz) * cfg["batch"]
+        hbm = {"achieved": alg_bytes / world / (ms_step * 1e-3) / 1e9, "peak": self.hbm_peak, "unit": "GB/s",
+               "peak_source": self.hbm_src}
+        if plan.axis_aligned or mode == 2:
+            roofline = {"bound": "hbm", "achieved": hbm["achieved"], "peak": self.hbm_peak, "unit": "GB/s",
+                        "frac": hbm["achieved"] / self.hbm_peak, "traffic": None, "peak_source": self.hbm_src,
+                        "algorithmic": "each source byte read once + each canvas byte written once (SURVEY 8d)"}
+        else:
+            F = flops_per_covered_pixel(plan.side, plan.cos_t, plan.sin_t, CH)
+            f32 = arith == aai.ARITH_F32
+            peak = self.fp32_nominal if f32 else self.fp64_nominal
+            achieved = F * covered / world / (ms_step * 1e-3) / 1e12
+            roofline = {"bound": "fp32" if f32 else "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                        "frac": achieved / peak, "traffic": None,
+                        "peak_source": f"nominal {self.n_sm} SMs x {128 if f32 else 64} lanes x 2 x {self.sm_max:.0f} MHz "
+                                       "(MEASURED_PEAKS.json holds no FP32/FP64 figure)",
+                        "algorithmic": f"{F:.0f} flop per covered canvas pixel x {covered / world:.0f} covered pixels per "
+                                       "launch (SURVEY 8d contract figure)",
+                        "hbm": hbm}
+            if f32:
+                roofline["peak_measured_ffma_probe"] = self.probe_fp32()
+        prof = self.latest.get(tag or f"cfg{cfg_id}", {})
         traffic = prof.get("dram_bytes_per_launch")
-        if traffic is not None and "per" in prof:  # profiled per slice of a batched launch: scale to this rank's launch
-            traffic = int(traffic * cfg["batch"] / world)
+        if traffic is not None:
+            if "per" in prof:  # profiled per slice of a batched launch: scale to this rank's launch
+                traffic = int(traffic * cfg["batch"] / world)
+            elif world > 1:
+                traffic = None  # captured on the whole canvas; a band's launch was not profiled
         roofline["traffic"] = traffic
-    except Exception:
-        pass
 
+        res = {
+            "workload": cfg["label"], "mode": {1: "area-average", 2: "fast"}[mode],
+            "dtype": "f32" if arith == aai.ARITH_F32 else "f64", "canvas": f"{plan.dst_w}x{plan.dst_h}",
+            "canvas_dtype": str(out_dt).replace("torch.", ""), "value": value, "unit": UNIT, "ms_per_step": ms_step,
+            "steps": steps, "gpu_launches": int(launches), "roofline": roofline, "covered_pixels": covered,
+            "timing": (f"inputs larger than L2 ({resident / 1e6:.0f} MB resident source per rank)" if resident > 130e6
+                       else "L2-resident input (source smaller than L2); latency bound"),
+        }
+        if world > 1:
+            res["band_ms"] = [round(v, 4) for v in band_ms]
+        if e2e is not None:
+            res["e2e"] = e2e
+        if verify is not None:
+            res["verified"] = verify["ok"]
+            res["verify"] = verify
+        if with_clocks:
+            res["clocks"] = {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")}
+        res["_plan"] = plan
+        res["_info"] = info
+        if peer is not None:
+            self.barrier()
+            peer.close()
+        del dev_src, dev_dst
+        torch.cuda.empty_cache()
+        return res
+
+    def _verify(self, cfg, cfg_id, plan, mode, arith, band, dev_dst, host_dst, step, seed, first_image):
+        """(a) the end-to-end canvas equals, bit for bit, the canvas computed from the HBM-generated source (the upload /
+        NVLink exchange delivered exactly the right bytes to the right rows); (b) first and last row of this rank's band
+        (first / last slice of a batch) against the CPU oracle."""
+        torch, aai = self.torch, self.aai
+        from area_average_interpolation_b200.synthetic import synthetic_image_torch
+
+        np_dt = np.dtype(cfg["dtype"])
+        f32 = arith == aai.ARITH_F32
+        ok, max_err, checked, same = True, 0.0, 0, None
+        try:
+            step()
+            torch.cuda.synchronize()
+            got = dev_dst.cpu()
+            if host_dst is not None:
+                if band is not None:
+                    same = bool(torch.equal(got, host_dst))
+                else:  # the host keeps `distinct` canvases; slice k landed in host_dst[k % distinct]
+                    n = host_dst.shape[0]
+                    same = bool(all(torch.equal(got[k], host_dst[k]) for k in range(n)))
+                ok = ok and same
+            got = got.numpy()
+            u8 = np_dt == np.uint8
+            if band is not None:
+                rows = sorted({band.row0, band.row1 - 1}) if band.rows > 0 else []
+                for r in rows:
+                    _, _, sy0, sy1 = aai.band_source_window(plan, r, r + 1)
+                    if sy1 <= sy0:
+                        want = np.zeros((1, plan.dst_w))
+                        chans = [0]
+                    else:
+                        src_rows = synthetic_image_torch(cfg["w"], cfg["h"], np_dt, seed, channels=cfg["ch"], y0=sy0,
+                                                         rows=sy1 - sy0, device=self.dev).cpu().numpy()
+                        chans = [0] if cfg["ch"] == 1 else [0, cfg["ch"] - 1]
+                    for c in chans:
+                        if sy1 > sy0:
+                            want = _verify_rows(src_rows, sy0, cfg, mode, (r, r + 1), c)
+                        g = got[r - band.row0][None, ...]
+                        g = (g[..., c] if cfg["ch"] > 1 else g).astype(np.float64)
+                        err = self._err(g, want, u8, f32)
+                        max_err = max(max_err, err)
+                        checked += 1
+            else:
+                for k in sorted({0, got.shape[0] - 1}):
+                    src_k = synthetic_image_torch(cfg["w"], cfg["h"], np_dt, seed + 1000 * (first_image + (k % 4)),
+                                                  device=self.dev).cpu().numpy()
+                    for r in (0, plan.dst_h // 2):
+                        want = _verify_rows(src_k, 0, cfg, mode, (r, r + 1), 0)
+                        err = self._err(got[k][r][None, :].astype(np.float64), want, u8, f32)
+                        max_err = max(max_err, err)
+                        checked += 1
+            ok = ok and max_err <= 1.0
+        except Exception as exc:
+            print(f"[bench] rank {self.rank}: verification failed to run: {exc!r}", file=sys.stderr)
+            ok = False
+        ok_all = self.min_over_ranks(1.0 if ok else 0.0) == 1.0
+        return {"ok": bool(ok_all), "e2e_bitwise_equals_device_path": same,
+                "oracle_rows_checked_per_rank": checked, "max_error_over_tolerance": self.max_over_ranks(max_err),
+                "tolerance": ("0.5 + 0.5/255 absolute (8-bit canvas, round half up)" if np_dt == np.uint8 else
+                              ("1e-5 relative (FP32 kernel)" if f32 else "1e-9 relative (FP64 arithmetic; float32 canvas "
+                                                                        "rounds to 6e-8)"))}
+
+    @staticmethod
+    def _err(got, want, u8, f32):
+        """max error / tolerance"""
+        if u8:
+            return float(np.abs(got - want).max() / (0.5 + 0.5 / 255.0))
+        rel = np.abs(got - want) / np.where(want == 0, 1.0, np.abs(want))
+        return float(rel.max() / (1e-5 if f32 else 1e-7))  # (a float32 canvas rounds the FP64 result to 6e-8)
+
+
+def our_arm(args, cfg_id):
+    b = Bench(args)
+    cfg = CONFIGS[cfg_id]
+    head = b.measure(cfg_id, arith_name=args.arith, mode=args.mode, with_e2e=True, with_verify=not args.no_verify)
+    plan, info = head.pop("_plan"), head.pop("_info")
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32" if arith == aai.ARITH_F32 else "f64", "data": "synthetic",
-        "config": {"workload": cfg["label"], "canvas": f"{plan.dst_w}x{plan.dst_h}", "scale": plan.scale,
-                   "footprint_side": plan.side, "sharding": ("row bands balanced by covered pixels" if cfg["batch"] == 1
-                                                             else "whole images per rank"),
-                   "timing": f"inputs larger than L2 ({resident_bytes / 1e6:.0f} MB resident source per rank)"
-                   if resident_bytes > 130e6 else "L2-resident input (source smaller than L2); latency bound",
-                   "covered_pixels": covered, "numa_node_rank0": numa,
-                   "e2e_source": ("each source row uploaded once by its owner rank, halos pulled over NVLink "
-                                  "(CUDA IPC peer copies, no NCCL on the data path)" if peer is not None else
-                                  "each rank uploads its band's source halo from pinned host memory (chunk-pipelined)")},
-        "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")},
-        "e2e": {"value": total_pixels / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d_total,
-                "d2h_bytes_per_step": d2h_total, "ms_per_step": e2e_ms},
-        "gpu_launches": int(launches),
-        "roofline": roofline,
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": b.world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",
+        "config": {"workload": cfg["label"], "canvas": head["canvas"], "canvas_dtype": head["canvas_dtype"],
+                   "scale": plan.scale, "footprint_side": plan.side, "mode": head["mode"],
+                   "sharding": ("row bands balanced by kernel cost" if cfg["batch"] == 1 else "whole images per rank"),
+                   "timing": head["timing"], "covered_pixels": head["covered_pixels"], "numa_node_rank0": b.numa,
+                   "e2e_source": info.get("e2e_source")},
+        "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+        "roofline": head["roofline"],
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if "band_ms" in head:
+        line["band_ms"] = head["band_ms"]
+    if "verified" in head:
+        line["verified"] = head["verified"]
+        line["verify"] = head["verify"]
+    if b.rank == 0 and b.world == 1 and not args.no_cpu_baseline:
         kind = cpu_kind()
         rep = replica_of(cfg, cfg["baseline_replica"])
-        n, sec = _ref_worker((rep["w"], rep["ratio"], rep["angle"], rep["iso"], seed, kind))
+        n, sec = _ref_worker((rep["w"], rep["ratio"], rep["angle"], rep["iso"], 20201 + cfg_id, kind))
         line["cpu_baseline"] = {
             "value": n / sec / 1e6, "unit": UNIT, "cores": 1, "kind": kind,
             "sample": f"one {rep['w']}x{rep['h']} float64 replica of the workload (same ratio/angle), {sec:.1f} s, "
                       "single thread as the reference ships"}
-    if rank == 0:
+    # ---- the other named shapes + the FP64 kernel + fast mode, same run, outside the headline's timed regions --------
+    if not args.no_extra:
+        extra = {}
+        k = max(3, min(args.steps, 10))
+        todo = [(f"cfg{c}", c, "auto", 1) for c in sorted(CONFIGS) if c != cfg_id]
+        todo += [(f"cfg{cfg_id}_f64", cfg_id, "f64", 1), (f"cfg{cfg_id}_fast", cfg_id, "auto", 2)]
+        for name, c, ar, mode in todo:
+            try:
+                r = b.measure(c, arith_name=ar, mode=mode, steps=k, with_e2e=(b.world == 1),
+                              with_verify=not args.no_verify, with_clocks=True, tag=name)
+                r.pop("_plan")
+                r.pop("_info")
+                extra[name] = r
+            except Exception as exc:
+                extra[name] = {"error": repr(exc)}
+                print(f"[bench] {name} failed: {exc!r}", file=sys.stderr)
+        line["configs"] = extra
+    if b.rank == 0:
         print(json.dumps(line), flush=True)
-    if peer is not None:
-        barrier()
-        peer.close()
-    if world > 1:
-        dist.destroy_process_group()
+    if b.world > 1:
+        b.dist.destroy_process_group()
     return 0
 
 
@@ -536,7 +681,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arith", default="auto", choices=["auto", "f64", "f32"],
                     help="auto: FP32 kernel for float32/8-bit images, FP64 kernel for float64 images")
+    ap.add_argument("--mode", type=int, default=1, choices=[1, 2], help="1 area average (headline), 2 fast mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="headline workload only (skip the `configs` record)")
+    ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-peer", action="store_true",
                     help="N>1: every rank uploads its whole halo from the host instead of NVLink peer copies")
     args = ap.parse_args()
@@ -549,7 +697,7 @@ def main():
     sys.stdout = os.fdopen(json_fd, "w")
     if args.impl == "reference":
         return reference_arm(args, cfg)
-    return our_arm(args, cfg)
+    return our_arm(args, args.config)
 
 
 if __name__ == "__main__":

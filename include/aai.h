@@ -198,6 +198,52 @@ int aai_run_host(const aai_plan *plan, int mode, int arith, const aai_image *src
 int aai_run_host_band(const aai_plan *plan, int mode, int arith, const aai_image *src, const aai_image *dst,
                       int64_t row0, int64_t row1, int device, void *stream, int synchronize);
 
+/* A batch of HOST images that share one plan (BASELINE config 5 end to end; a CT volume): the slices are uploaded,
+ * resampled and downloaded in a pipeline of three streams -- groups of slices go through a ring of device buffers, each
+ * group is ONE batched kernel launch (aai_run_device_batch), and group g's upload / kernel / download overlap the
+ * neighbouring groups' (PCIe is full duplex).  Whole images; srcs[k] / dsts[k] may be any host buffers (use pinned
+ * memory for truly asynchronous copies).  `stream` / `synchronize` as in aai_run_host_band. */
+int aai_run_host_batch(const aai_plan *plan, int mode, int arith, const aai_image *srcs, const aai_image *dsts,
+                       int n_images, int device, void *stream, int synchronize);
+
+/* ---- peer group: ONE large image over one process per GPU, end to end (NVLink halo option) ------------
+ *
+ * With plain row bands every rank would upload its whole source halo from the host -- about half of the image per rank
+ * for a rotated canvas, i.e. N/2 images over PCIe in total.  In a peer group every source row crosses PCIe exactly once:
+ * rank r owns source rows [H r/N, H (r+1)/N), uploads them in chunks into its own full-size device image, and every
+ * rank pulls the rows of its halo that it does not own out of the owners' device images with peer copies over NVLink
+ * (CUDA IPC memory mappings) AS THE CHUNKS LAND: the device-side dependency "chunk c of owner p has arrived" is an
+ * interprocess CUDA event (cudaIpcGetEventHandle) that the reader's copy stream waits on.  There is no NCCL and no
+ * barrier per step; the host side only orders the *enqueueing* (a reader may only wait on an event once its owner has
+ * re-recorded it for this step) through two counters per rank in a small POSIX shared-memory segment.  Kernel and
+ * download of the band are chunk-pipelined behind the pulls, so a step costs about the slowest upload plus a short tail.
+ *
+ * Set-up (once per plan / image type): every rank calls aai_peer_create, exchanges the AAI_PEER_BLOB_BYTES blob of
+ * aai_peer_export with all ranks through ANY out-of-band channel (MPI, a torch.distributed object gather, files), and
+ * calls aai_peer_connect with the world_size blobs in rank order.  Then aai_peer_run per step.  Results are bitwise
+ * identical to one GPU (all ranks share the plan). */
+typedef struct aai_peer aai_peer;
+#define AAI_PEER_BLOB_BYTES 2048
+int aai_peer_create(const aai_plan *plan, int32_t dtype, int32_t channels, int rank, int world_size, int device,
+                    aai_peer **out);
+int aai_peer_export(aai_peer *peer, unsigned char blob[AAI_PEER_BLOB_BYTES]);
+int aai_peer_connect(aai_peer *peer, const unsigned char *blobs_of_all_ranks);
+/* Source rows [*y0, *y1) this rank uploads; canvas rows [*row0, *row1) it computes (aai_partition_rows). */
+int aai_peer_owned_rows(const aai_peer *peer, int64_t *y0, int64_t *y1);
+int aai_peer_band(const aai_peer *peer, int64_t *row0, int64_t *row1);
+/* One step: `host_src` holds (at least) the owned source rows, `host_dst` receives the band's canvas rows (each may be
+ * a band view: y0/rows).  Enqueued on `stream` (NULL = an internal stream, blocking); returns without waiting unless
+ * `synchronize`.  All ranks must call it the same number of times; a rank waits (on the host, bounded) until the ranks
+ * it exchanges rows with have entered the same step. */
+int aai_peer_run(aai_peer *peer, int mode, int arith, const aai_image *host_src, const aai_image *host_dst,
+                 void *stream, int synchronize);
+/* The rank's full-size device source image (rows of the band's halo are valid after a step) -- for device-resident
+ * follow-up work (aai_run_device). */
+int aai_peer_device_source(const aai_peer *peer, aai_image *out);
+/* Frees the group's device memory and IPC mappings.  Call it once every rank has completed its last step (any barrier
+ * of the launcher): peers read this rank's device image. */
+int aai_peer_destroy(aai_peer *peer);
+
 /* Kernel-launch counter of this process (every overlap / separable / fast kernel launch increments it). */
 int64_t aai_launch_count(void);
 

@@ -43,7 +43,9 @@ def test_only_tests_smoke_and_bench_baseline_legs_use_the_oracle():
         assert len(m.group(1)) > 0, "bench.py imports the oracle at module level"
         head = src[:m.start()]
         func = re.findall(r"^def (\w+)\(", head, re.M)[-1]
-        assert func in ("_ref_worker", "cpu_kind"), func  # the cpu_baseline leg and the reference arm call only these
+        # the cpu_baseline leg and the reference arm call only the first two; _verify_rows is the checker of the `verified`
+        # flag (oracle rows against the canvas the timed path produced, outside every timed region)
+        assert func in ("_ref_worker", "cpu_kind", "_verify_rows"), func
 
 
 def test_bench_fails_loudly_without_a_gpu():

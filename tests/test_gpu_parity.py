@@ -670,3 +670,198 @@ def test_full_size_cfg5_slice_axis_aligned(aai, oracle):
     k = np.array([0.5, 1.0, 0.5])
     want = (s[2 * y - 1:2 * y + 2, 2 * x - 1:2 * x + 2] * np.outer(k, k)).sum() / 4.0
     assert abs(out[y, x] - want) <= 1e-9 * abs(want)
+
+
+# ---- BASELINE shapes at FULL size on the benchmarked paths (VERDICT r1 "missing" 1) ----------------------------------
+
+def _f32_err(got, want):
+    """Relative error of an FP32-kernel result (absolute where the reference value is exactly 0)."""
+    return rel_err(np.asarray(got, dtype=np.float64), want)
+
+
+def test_full_size_cfg1_u8_whole_image(aai, oracle):
+    """BASELINE config 1 at full size (512^2 8-bit, 0.5x, 0 deg, iso 256): the WHOLE canvas against the oracle --
+    FP64 arithmetic bit-exact (weights 1/2, 1, 1/2 are exact), FP32 arithmetic f32 and u8 destinations (the path
+    bench.py times: TMA separable kernel, u8 source)."""
+    from area_average_interpolation_b200.synthetic import synthetic_image
+
+    src = synthetic_image(512, 512, np.uint8, 20201 + 1)
+    st, want, wiso = oracle.run(src, 1.0, 0.5, (256.0, 256.0), 0.0)
+    assert st == 0 and want.shape == (256, 256)
+    r64 = _run(aai, src, 1.0, 0.5, (256.0, 256.0), 0.0)
+    assert r64.dst_isocenter == wiso and np.array_equal(r64.dst, want)
+    r32 = _run(aai, src, 1.0, 0.5, (256.0, 256.0), 0.0, arith=aai.ARITH_F32, out_dtype=np.float32)
+    assert np.abs(r32.dst.astype(np.float64) - want).max() <= TOL_U8_ABS
+    r8 = _run(aai, src, 1.0, 0.5, (256.0, 256.0), 0.0, arith=aai.ARITH_F32, out_dtype=np.uint8)
+    assert np.abs(r8.dst.astype(np.float64) - want).max() <= 0.5 + TOL_U8_ABS  # round half up of the real value
+
+
+def test_full_size_cfg2_u8_whole_image(aai, oracle):
+    """BASELINE config 2 at full size (2048^2 8-bit, 0.37x, 30 deg, iso 1024 -> 1035^2): the WHOLE canvas against the
+    oracle, FP64 kernel <= 1e-9 relative, FP32 kernel (u8 source; f32 and u8 destinations) <= 0.5/255 absolute."""
+    from area_average_interpolation_b200.synthetic import synthetic_image
+
+    src = synthetic_image(2048, 2048, np.uint8, 20201 + 2)
+    st, want, wiso = oracle.run(src, 1.0, 0.37, (1024.0, 1024.0), 30.0)
+    assert st == 0 and want.shape == (1035, 1035)
+    r64 = _run(aai, src, 1.0, 0.37, (1024.0, 1024.0), 30.0)
+    assert r64.dst_isocenter == wiso
+    e64 = rel_err(r64.dst, want)
+    assert e64.max() <= TOL_F64_REL, (float(e64.max()), int((e64 > TOL_F64_REL).sum()))
+    r32 = _run(aai, src, 1.0, 0.37, (1024.0, 1024.0), 30.0, arith=aai.ARITH_F32, out_dtype=np.float32)
+    e = np.abs(r32.dst.astype(np.float64) - want)
+    assert e.max() <= TOL_U8_ABS, (float(e.max()), int((e > TOL_U8_ABS).sum()))
+    assert ((r32.dst == 0) == (want == 0)).all()  # the same canvas pixels are covered
+    r8 = _run(aai, src, 1.0, 0.37, (1024.0, 1024.0), 30.0, arith=aai.ARITH_F32, out_dtype=np.uint8)
+    assert np.abs(r8.dst.astype(np.float64) - want).max() <= 0.5 + TOL_U8_ABS
+
+
+def test_full_size_cfg3_8192_rgb_u8_sample_rows(aai, oracle):
+    """BASELINE config 3 at FULL size: 8192^2 RGB 8-bit, 1.7x, 45 deg -> scale 3, expanded frame 24576^2 (where the 32-bit
+    multiply-high division and the int32 offsets live), canvas 19695^2 x 3.  First / middle / last rows, all three
+    channels, against the oracle, for the f32 AND the u8 destination (the one bench.py times)."""
+    import torch
+
+    from area_average_interpolation_b200.synthetic import synthetic_image
+
+    W = 8192
+    iso = (4095.5, 4095.5)
+    plan = aai.make_plan(W, W, 1.0, 1.7, iso, 45.0)
+    assert plan.scale == 3 and (plan.mod_w, plan.dst_w, plan.dst_h) == (24576, 19695, 19695)
+    src = synthetic_image(W, W, np.uint8, 20201 + 3, channels=3)
+    src_t = torch.from_numpy(src).cuda()
+    rows = (0, 1, 9847, 9848, 13001, plan.dst_h - 2, plan.dst_h - 1)
+    out8 = _device_run(aai, plan, src_t, torch.uint8, arith=aai.ARITH_F32)
+    got8 = {r: out8[r].cpu().numpy() for r in rows}
+    covered8 = int((out8[..., 0] != 0).sum().item())
+    del out8
+    out32 = _device_run(aai, plan, src_t, torch.float32, arith=aai.ARITH_F32)
+    got32 = {r: out32[r].cpu().numpy() for r in rows}
+    del out32
+    torch.cuda.empty_cache()
+    assert 0.49 < covered8 / (plan.dst_w * plan.dst_h) < 0.51  # SURVEY §8: covered fraction 0.500 (u8 zeros are rare)
+    for r in rows:
+        for c in range(3):
+            st, want, _ = oracle.run(src, 1.0, 1.7, iso, 45.0, rows=(r, r + 1), channel=c)
+            assert st == 0
+            e = np.abs(got32[r][None, :, c].astype(np.float64) - want)
+            assert e.max() <= TOL_U8_ABS, (r, c, float(e.max()))
+            e8 = np.abs(got8[r][None, :, c].astype(np.float64) - want)
+            assert e8.max() <= 0.5 + TOL_U8_ABS, (r, c, float(e8.max()))
+
+
+def test_full_size_cfg5_fp32_slice_and_64_slice_stack(aai, oracle):
+    """BASELINE config 5 on the path bench.py times: FP32 arithmetic, TMA separable kernel.  (a) one full 4096^2 float32
+    slice, WHOLE canvas against the oracle; (b) a stack of 64 equally strided slices through aai_run_device_batch (one
+    launch, rank-3 tensor map): slices 0 / 31 / 63 x 4 rows against the oracle, and slice 0 bitwise equal to (a)."""
+    import torch
+
+    from area_average_interpolation_b200.synthetic import synthetic_image
+
+    W, N = 4096, 64
+    iso = (2048.0, 2048.0)
+    plan = aai.make_plan(W, W, 1.0, 0.5, iso, 0.0)
+    assert plan.axis_aligned == 1 and (plan.dst_w, plan.dst_h) == (2048, 2048)
+    base = [synthetic_image(W, W, np.float32, 20201 + 5 + 1000 * k) for k in range(2)]
+
+    def host_slice(k):  # slice k of the stack: a base slice rolled by 37 k rows (cheap to reproduce on the host)
+        return np.roll(base[k % 2], 37 * k, axis=0)
+
+    # (a) one slice, whole canvas
+    s0 = torch.from_numpy(base[0]).cuda()
+    one = _device_run(aai, plan, s0, torch.float32, arith=aai.ARITH_F32)
+    st, want, _ = oracle.run(base[0], 1.0, 0.5, iso, 0.0)
+    assert st == 0
+    e = _f32_err(one.cpu().numpy(), want)
+    assert e.max() <= TOL_F32_REL, (float(e.max()), int((e > TOL_F32_REL).sum()))
+    # (b) the stack
+    dev_base = [torch.from_numpy(b).cuda() for b in base]
+    stack = torch.empty((N, W, W), dtype=torch.float32, device="cuda")
+    for k in range(N):
+        stack[k] = torch.roll(dev_base[k % 2], 37 * k, dims=0)
+    dst = torch.full((N, plan.dst_h, plan.dst_w), -1.0, dtype=torch.float32, device="cuda")
+    before = aai.launch_count()
+    aai.run_device_batch(plan, [aai.tensor_image(stack[k]) for k in range(N)],
+                         [aai.tensor_image(dst[k]) for k in range(N)], arith=aai.ARITH_F32,
+                         stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert aai.launch_count() == before + 1
+    assert torch.equal(dst[0], one)
+    for k in (0, 31, 63):
+        hs = host_slice(k)
+        assert np.array_equal(stack[k, 100:102].cpu().numpy(), hs[100:102])
+        got = dst[k].cpu().numpy()
+        for row in (0, 777, 1024, 2047):
+            st, want, _ = oracle.run(hs, 1.0, 0.5, iso, 0.0, rows=(row, row + 1))
+            e = _f32_err(got[row:row + 1], want)
+            assert e.max() <= TOL_F32_REL, (k, row, float(e.max()))
+
+
+# ---- host-buffer copies, very tall canvases, several devices ------------------------------------------------------------
+
+def test_download_into_a_column_view_leaves_the_rest_of_the_array_untouched(aai):
+    """a host image may be a column view of a wider array; copies must not touch the bytes between rows --
+    also when the view's row stride happens to equal the device pitch."""
+    import torch
+
+    w, h = 100, 40  # device pitch of 100 floats = 512 bytes = 128 floats
+    big = np.full((h, 128), -7.0, dtype=np.float32)
+    view = big[:, :w]
+    host = np.random.default_rng(3).uniform(0, 1, size=(h, w)).astype(np.float32)
+    d = aai.image_alloc(0, w, h, aai.F32)
+    assert d.pitch_bytes == big.strides[0]
+    aai.image_upload(d, aai._host_image(host))
+    aai.image_download(aai._host_image(view), d)
+    torch.cuda.synchronize()
+    assert np.array_equal(view, host)
+    assert (big[:, w:] == -7.0).all()
+    # the same through the end-to-end host call: dst is a view into a wider array
+    plan = aai.make_plan(64, 64, 1.0, 0.5, (32.0, 32.0), 20.0)
+    wide = np.full((plan.dst_h, plan.dst_w + 29), -3.0, dtype=np.float64)
+    src = np.random.default_rng(4).uniform(0, 100, size=(64, 64))
+    aai.run_host(plan, src, wide[:, :plan.dst_w])
+    assert (wide[:, plan.dst_w:] == -3.0).all() and (wide[:, :plan.dst_w] != -3.0).all()
+    aai.image_free(d, 0)
+
+
+def test_canvas_taller_than_the_grid_limit(aai, oracle):
+    """rows sit on grid.y (<= 65535 CTAs of 8 rows); a line scan with a canvas taller than 524 280 rows is
+    cut into several launches instead of failing."""
+    import torch
+
+    w, h = 3, 530000
+    rng = np.random.default_rng(6)
+    src = rng.uniform(0, 4096, size=(h, w)).astype(np.float32)
+    src_t = torch.from_numpy(src).cuda()
+    for angle, mode, arith in ((0.0, 1, aai.ARITH_F32), (0.0, 2, aai.ARITH_F32), (180.0, 1, aai.ARITH_F64)):
+        plan = aai.make_plan(w, h, 1.0, 1.0, (1.0, 265000.0), angle)
+        assert plan.status == 0 and plan.dst_h > 65535 * 8
+        before = aai.launch_count()
+        out = _device_run(aai, plan, src_t, torch.float64, arith=arith, mode=mode)
+        assert aai.launch_count() >= before + 2
+        for r0 in (0, 65535 * 8 - 2, plan.dst_h - 3):
+            st, want, _ = oracle.run(src, 1.0, 1.0, (1.0, 265000.0), angle, mode=mode, rows=(r0, r0 + 3))
+            assert st == 0
+            got = out[r0:r0 + 3].cpu().numpy()
+            if mode == 2:  # centre-in ties at exactly symmetric geometry are decided by rounding noise (see fast-mode tests)
+                assert (rel_err(got, want) <= 1e-5).mean() > 0.6
+            else:
+                assert rel_err(got, want).max() <= (TOL_F32_REL if arith == aai.ARITH_F32 else TOL_F64_REL), (angle, r0)
+
+
+def test_several_devices_reproduce_one_device_bitwise(aai, oracle):
+    """T6 on real hardware: aai_run_host over ALL devices of the box (one band + halo per device, one host thread each)
+    is bitwise identical to device 0 alone -- FP64 and FP32 kernels, rotated and axis-aligned.  Needs >= 2 GPUs
+    (`gpurun --gpus 2`); the 1-GPU box skips it (bench.py's `verified` flag covers the one-process-per-GPU path)."""
+    n = aai.device_count()
+    if n < 2:
+        pytest.skip("needs at least two CUDA devices")
+    rng = np.random.default_rng(8)
+    src = rng.uniform(0, 4096, size=(1500, 2000)).astype(np.float32)
+    for (ratio, angle, iso) in [(0.37, 17.3, (1000.0, 750.0)), (0.5, 0.0, (1000.0, 750.0)), (1.7, 117.0, (999.5, 749.5))]:
+        for arith, od in ((aai.ARITH_F64, np.float64), (aai.ARITH_F32, np.float32)):
+            one = _run(aai, src, 1.0, ratio, iso, angle, arith=arith, out_dtype=od, devices=[0])
+            many = _run(aai, src, 1.0, ratio, iso, angle, arith=arith, out_dtype=od, devices=list(range(n)))
+            assert np.array_equal(one.dst, many.dst), (ratio, angle, arith)
+        st, want, _ = oracle.run(src, 1.0, ratio, iso, angle, rows=(700, 704))
+        assert rel_err(many.dst[700:704], want).max() <= TOL_F32_REL
