@@ -147,6 +147,40 @@ __device__ __forceinline__ void pixel_f64(const AaiKernelParams &kp, double cx, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Fast mode (Source.cpp:866-907): unweighted mean of the expanded pixels whose CENTRE lies in the footprint.
+// ------------------------------------------------------------------------------------------------------------
+// FP64 evaluation of one canvas pixel (also the precision fallback of the FP32 fast kernel)
+template <typename TI, int NC>
+__device__ __forceinline__ void pixel_fast_f64(const AaiKernelParams &kp, int x, int y, int &count, double (&acc)[NC]) {
+    double cx, cy;
+    pixel_centre(kp, x, y, cx, cy);
+    int wx0, wx1, wy0, wy1;
+    search_window(kp, cx, cy, wx0, wx1, wy0, wy1);
+    const double ext = kp.hb + 1e-6;
+    const int ix0 = max(wx0, __double2int_ru(cx - ext)), ix1 = min(wx1, __double2int_rd(cx + ext));
+    const int jy0 = max(wy0, __double2int_ru(cy - ext)), jy1 = min(wy1, __double2int_rd(cy + ext));
+    count = 0;
+#pragma unroll
+    for (int ch = 0; ch < NC; ++ch) acc[ch] = 0.0;
+    for (int j = jy0; j <= jy1; ++j) {
+        const double ry = (double)j - cy;
+        for (int i = ix0; i <= ix1; ++i) {
+            const double rx = (double)i - cx;
+            const double u0 = rx * kp.shape.cs - ry * kp.shape.sn;
+            const double v0 = rx * kp.shape.sn + ry * kp.shape.cs;
+            if (fabs(u0) <= kp.shape.half && fabs(v0) <= kp.shape.half) {  // closed point-in-square (837-864)
+                int sx, sy;
+                mod_to_src(kp, i, j, sx, sy);
+                const char *row = (const char *)kp.src + (int64_t)(sy - src_row0(kp)) * kp.src_pitch;
+                count += 1;
+#pragma unroll
+                for (int ch = 0; ch < NC; ++ch) acc[ch] += SrcLoad<TI>::get(row, sx * NC + ch);
+            }
+        }
+    }
+}
+
 // Cells that can have non-zero overlap: |i - cx| < hb + 1/2, clamped to the image.  The reference's search window
 // (Source.cpp:426-429, search_window() above) always contains this range -- its half width L*sqrt(2)/2 + 1 is at
 // least hb + 1/2 = L(c+s)/2 + 1/2 and it is clamped to the same image bounds -- so intersecting with it is a no-op and

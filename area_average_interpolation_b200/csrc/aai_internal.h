@@ -70,6 +70,11 @@ int aai_launch_overlap_f32_n4(const AaiKernelParams &kp, int src_dtype, int dst_
 int aai_launch_overlap_f32_n5(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_overlap_f32_n6(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_overlap_f32_n8(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
+// fast mode, FP32 arithmetic, unrolled (same translation units): float / 8-bit images with 1 or 3 channels
+int aai_launch_fast_f32_n4(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
+int aai_launch_fast_f32_n5(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
+int aai_launch_fast_f32_n6(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
+int aai_launch_fast_f32_n8(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
 // aai_kernels_f64.cu, likewise (unrolled FP64 kernel; cudaErrorNotSupported -> the rolled kernel in aai_kernels.cu)
 int aai_launch_overlap_f64_n4(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_overlap_f64_n5(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);

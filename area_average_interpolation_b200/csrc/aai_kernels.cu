@@ -92,37 +92,6 @@ __global__ void __launch_bounds__(TILE_W *TILE_H)
 // ------------------------------------------------------------------------------------------------------------
 // Fast mode (Source.cpp:866-907): unweighted mean of the expanded pixels whose CENTRE lies in the footprint.
 // ------------------------------------------------------------------------------------------------------------
-// FP64 evaluation of one canvas pixel (also the precision fallback of the FP32 fast kernel)
-template <typename TI, int NC>
-__device__ __forceinline__ void pixel_fast_f64(const AaiKernelParams &kp, int x, int y, int &count, double (&acc)[NC]) {
-    double cx, cy;
-    pixel_centre(kp, x, y, cx, cy);
-    int wx0, wx1, wy0, wy1;
-    search_window(kp, cx, cy, wx0, wx1, wy0, wy1);
-    const double ext = kp.hb + 1e-6;
-    const int ix0 = max(wx0, __double2int_ru(cx - ext)), ix1 = min(wx1, __double2int_rd(cx + ext));
-    const int jy0 = max(wy0, __double2int_ru(cy - ext)), jy1 = min(wy1, __double2int_rd(cy + ext));
-    count = 0;
-#pragma unroll
-    for (int ch = 0; ch < NC; ++ch) acc[ch] = 0.0;
-    for (int j = jy0; j <= jy1; ++j) {
-        const double ry = (double)j - cy;
-        for (int i = ix0; i <= ix1; ++i) {
-            const double rx = (double)i - cx;
-            const double u0 = rx * kp.shape.cs - ry * kp.shape.sn;
-            const double v0 = rx * kp.shape.sn + ry * kp.shape.cs;
-            if (fabs(u0) <= kp.shape.half && fabs(v0) <= kp.shape.half) {  // closed point-in-square (837-864)
-                int sx, sy;
-                mod_to_src(kp, i, j, sx, sy);
-                const char *row = (const char *)kp.src + (int64_t)(sy - src_row0(kp)) * kp.src_pitch;
-                count += 1;
-#pragma unroll
-                for (int ch = 0; ch < NC; ++ch) acc[ch] += SrcLoad<TI>::get(row, sx * NC + ch);
-            }
-        }
-    }
-}
-
 template <typename TI, typename TO, int NC>
 __global__ void __launch_bounds__(TILE_W *TILE_H) fast_kernel(const __grid_constant__ AaiKernelParams kp) {
     const int x = blockIdx.x * TILE_W + threadIdx.x;
@@ -347,7 +316,15 @@ int aai_launch_expand(const AaiKernelParams &kp, int elem_bytes, void *stream) {
 
 int aai_launch_fast(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream) {
     // FP32 arithmetic on request for float / 8-bit sources (the mean of 8-byte doubles stays in FP64)
-    const bool f32 = arith == AAI_ARITH_F32 && src_dtype != AAI_F64 && dst_dtype != AAI_F64 &&
-                     (uint64_t)(kp.mod_w > kp.mod_h ? kp.mod_w : kp.mod_h) < (1u << 30);
+    const uint64_t max_e = (uint64_t)(kp.mod_w > kp.mod_h ? kp.mod_w : kp.mod_h);
+    const bool f32 = arith == AAI_ARITH_F32 && src_dtype != AAI_F64 && dst_dtype != AAI_F64 && max_e < (1u << 30);
+    // unrolled kernel: at most floor(2 hb + ~1e-5) + 1 lattice points per axis lie within hb of a footprint centre
+    if (f32 && (kp.channels == 1 || kp.channels == 3) && max_e * (uint64_t)kp.scale < 0x100000000ULL) {
+        const int nf = (int)floor(2.0 * ((double)kp.shapef.hb + 4e-6) + 1e-6) + 1;
+        if (nf <= 3) return aai_launch_fast_f32_n4(kp, src_dtype, dst_dtype, stream);
+        if (nf <= 4) return aai_launch_fast_f32_n5(kp, src_dtype, dst_dtype, stream);
+        if (nf <= 5) return aai_launch_fast_f32_n6(kp, src_dtype, dst_dtype, stream);
+        if (nf <= 7) return aai_launch_fast_f32_n8(kp, src_dtype, dst_dtype, stream);
+    }
     return (int)launch_any(f32 ? K_FAST_F32 : K_FAST, kp, src_dtype, dst_dtype, (cudaStream_t)stream);
 }

@@ -32,15 +32,6 @@ constexpr int MAXN = AAI_MAXN;
 #ifndef AAI_ROW_UNROLL
 #define AAI_ROW_UNROLL 1
 #endif
-#ifndef AAI_EXP_RY_INC
-#define AAI_EXP_RY_INC 0
-#endif
-#ifndef AAI_EXP_ROW2
-#define AAI_EXP_ROW2 0
-#endif
-#ifndef AAI_EXP_EDGE_CSE
-#define AAI_EXP_EDGE_CSE 0
-#endif
 constexpr int kRowUnroll = AAI_ROW_UNROLL;
 // Columns that every interior footprint of this translation unit touches: a footprint box of side 2 ext holds at least
 // floor(2 ext) lattice columns, and the host picks the smallest MAXN >= floor(2 ext) + 1 (MAXN = 8 also serves
@@ -138,22 +129,13 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
 #pragma unroll
         for (int k = 0; k + 1 <= MAXN; k += 2) {  // two grid lines per packed instruction
             AaiF2 t2, b2;
-#if AAI_EXP_EDGE_CSE  // experiment (default off): one expression for a column boundary everywhere, so that the boundaries
-                      // of the chords, of the top sides and of the row body are common subexpressions (~10 FADD/pixel)
-            aai_chord_v_f32x2(g, aai_f2((rx0 + (float)k) - 0.5f, (rx0 + (float)(k + 1)) - 0.5f), t2, b2);
-#else
             aai_chord_v_f32x2(g, aai_f2(rx0 + ((float)k - 0.5f), rx0 + ((float)k + 0.5f)), t2, b2);
-#endif
             yt[k] = t2.x;
             yt[k + 1] = t2.y;
             yb[k] = b2.x;
             yb[k + 1] = b2.y;
         }
-#if AAI_EXP_EDGE_CSE
-        if ((MAXN + 1) & 1) aai_chord_v_f32(g, (rx0 + (float)MAXN) - 0.5f, yt[MAXN], yb[MAXN]);
-#else
         if ((MAXN + 1) & 1) aai_chord_v_f32(g, rx0 + ((float)MAXN - 0.5f), yt[MAXN], yb[MAXN]);
-#endif
         float xlT, xrT;  // chord of the footprint on the row's top grid line
         const float t0 = ((float)dj0 - fy) - 0.5f;  // top of row 0
         aai_chord_h_f32(g, t0, xlT, xrT);
@@ -200,11 +182,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         // lengths of the cells' top sides inside the footprint: the previous row's bottom sides
         float lenTop[MAXN];
 #pragma unroll
-#if AAI_EXP_EDGE_CSE
-        for (int k = 0; k < MAXN; ++k) lenTop[k] = aai_overlap1_f32(xlT, xrT, (rx0 + (float)k) - 0.5f);
-#else
         for (int k = 0; k < MAXN; ++k) lenTop[k] = aai_overlap1_f32(xlT, xrT, e0 + (float)k);
-#endif
         // Source values are fetched one row ahead of their use (the loads of row r+1 are in flight while the areas of
         // row r are computed): the accumulate at the end of a row never waits for its own row's loads.
         // (Single-channel kernels only: three channels would need 30 staging registers.)
@@ -227,11 +205,6 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             }
         };
         if (PREFETCH) fetch(0, buf);
-#if AAI_EXP_RY_INC == 1
-        float ry_run = (float)dj0 - fy;
-#elif AAI_EXP_RY_INC == 2
-        float ry_run = (float)dj0;
-#endif
         // one row of cells: `cur` holds this row's source values (PREFETCH), `nxt` receives the next row's
         auto row = [&](int r, float (&cur)[MAXN][NC], float (&nxt)[MAXN][NC]) {
             if (PREFETCH) {
@@ -241,15 +214,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             }
             float rowA = 0.0f, rowB = 0.0f;  // GROUPED: this row's area in the first / second source column
             const bool top = (rowTop >> r) & 1u;
-#if AAI_EXP_RY_INC == 1  // experiment (default off): carried row offset, one FADD instead of I2F + FADD
-            const float ry = ry_run;
-            ry_run += 1.0f;
-#elif AAI_EXP_RY_INC == 2  // variant with bit-identical results: the integer row index carried as a float (exact)
-            const float ry = ry_run - fy;
-            ry_run += 1.0f;
-#else
             const float ry = (float)(dj0 + r) - fy;
-#endif
             float xlB, xrB;
             aai_chord_h_f32(g, ry + 0.5f, xlB, xrB);
             const float ey = ry - 0.5f;
@@ -311,13 +276,6 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 W11 += top ? 0.0f : rowB;
             }
         };
-#if AAI_EXP_ROW2  // experiment (default off): two rows per iteration, the two value buffers swap roles
-        float buf2[MAXN][NC];
-        for (int r = 0; r < nrows; r += 2) {
-            row(r, buf, buf2);
-            if (r + 1 < nrows) row(r + 1, buf2, buf);
-        }
-#else
 #pragma unroll kRowUnroll
         for (int r = 0; r < nrows; ++r) {
             float nxt[MAXN][NC];
@@ -329,7 +287,6 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                     for (int ch = 0; ch < NC; ++ch) buf[k][ch] = nxt[k][ch];
             }
         }
-#endif
         // Total overlap: the exact areas of a footprint inside the image add up to L^2 (border pixels never get here).
         sumA = g.area_total;
         // The reference's shape-2/4 quirk: one pair of corrected cells per minor-axis grid line crossed by a left/right
@@ -444,6 +401,133 @@ cudaError_t launch1(const AaiKernelParams &kp, int dst_dtype, cudaStream_t strea
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Fast mode (fastAreaAverageInterpolation, Source.cpp:866-907), FP32 arithmetic, unrolled: the unweighted mean of the
+// expanded pixels whose CENTRE lies in the footprint (closed point-in-square test, 837-864).
+//
+// HBM-bound by contract (each source byte once + each canvas byte once), so the kernel only has to stay out of the
+// way: at most NF = MAXN - 1 lattice points per axis can lie within h(c+s) of the footprint centre, all NF x NF
+// candidates are loaded unconditionally up front (independent loads in flight together; the footprints of a warp's
+// 16 x 2 canvas pixels overlap, L1 serves most of them) and tested branch-free -- two FFMAs for the footprint-local
+// coordinates, margin m = min(h - |u|, h - |v|), predicated adds.  The inside test is a discontinuous decision: as in
+// the overlap kernel the centre is split into lattice point + FP32 fraction, the smallest |m| of the pixel is tracked,
+// and a pixel with a margin inside the guard band -- or whose candidate box the image border clips -- is redone in FP64
+// (pixel_fast_f64, the reference's own centre expression).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int NF = MAXN - 1;
+template <typename TI, typename TO, int NC, bool IDENT>
+__global__ void __launch_bounds__(TILE_W *TILE_H, 1024 / (TILE_W * TILE_H))
+    fast_kernel_f32u(const __grid_constant__ AaiKernelParams kp) {
+    const int x = blockIdx.x * TILE_W + threadIdx.x;
+    const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
+    if (x >= kp.dst_w || y >= kp.row1) return;
+    const double cx = fma((double)x, kp.aff_xx, fma((double)y, kp.aff_xy, kp.aff_x0));
+    const double cy = fma((double)x, kp.aff_yx, fma((double)y, kp.aff_yy, kp.aff_y0));
+    const int irx = __double2int_rn(cx), iry = __double2int_rn(cy);
+    const float fx = (float)(cx - (double)irx), fy = (float)(cy - (double)iry);
+    const AaiShapeF &g = kp.shapef;
+    constexpr float tau = 4e-6f;
+    // lattice points whose centre can lie in the footprint: |i - cx| <= h(c+s) (FP32 with a safety margin)
+    const float ext = g.hb + tau;
+    const int bx0 = irx + __float2int_ru(fx - ext), bx1 = irx + __float2int_rd(fx + ext);
+    const int by0 = iry + __float2int_ru(fy - ext), by1 = iry + __float2int_rd(fy + ext);
+    char *drow = (char *)kp.dst + (int64_t)(y - dst_row0(kp)) * kp.dst_pitch;
+    if (bx1 < 0 || by1 < 0 || bx0 > kp.mod_w - 1 || by0 > kp.mod_h - 1) {  // no candidate in the image: count 0 -> 0
+#pragma unroll
+        for (int ch = 0; ch < NC; ++ch) store_f<TO>(drow, x * NC + ch, 0.0f);
+        return;
+    }
+    // the unrolled NF x NF block starts at (bx0, by0); it must lie inside the image (else: FP64 path below)
+    const bool inside_img = bx0 >= 0 && by0 >= 0 && bx0 + NF - 1 <= kp.mod_w - 1 && by0 + NF - 1 <= kp.mod_h - 1 &&
+                            bx1 - bx0 < NF && by1 - by0 < NF;
+    float count = 0.0f, acc[NC], worst = 1.0f;
+#pragma unroll
+    for (int ch = 0; ch < NC; ++ch) acc[ch] = 0.0f;
+    if (inside_img) {
+        constexpr int ESZ = (int)sizeof(TI) * NC;
+        const bool swapped = kp.e_axi == 0;
+        auto div_s = [&](int e) -> int64_t {
+            return (int64_t)(kp.scale != 1 ? __umulhi((unsigned)e, kp.div_magic) : (unsigned)e);
+        };
+        int64_t coff[NF], roff[NF];
+        if (IDENT) {
+#pragma unroll
+            for (int k = 0; k < NF; ++k) {
+                coff[k] = (int64_t)(bx0 + k) * ESZ;
+                roff[k] = (int64_t)(by0 + k - src_row0(kp)) * kp.src_pitch;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NF; ++k) {
+                const int i = bx0 + k, j = by0 + k;
+                coff[k] = swapped ? (div_s(kp.e_ayi * i + kp.e_ay0) - src_row0(kp)) * kp.src_pitch
+                                  : div_s(kp.e_axi * i + kp.e_ax0) * ESZ;
+                roff[k] = swapped ? div_s(kp.e_axj * j + kp.e_ax0) * ESZ
+                                  : (div_s(kp.e_ayj * j + kp.e_ay0) - src_row0(kp)) * kp.src_pitch;
+            }
+        }
+        const float rx0 = (float)(bx0 - irx) - fx, ry0 = (float)(by0 - iry) - fy;
+#pragma unroll
+        for (int r = 0; r < NF; ++r) {
+            float v[NF][NC];
+            const char *rowp = (const char *)kp.src + roff[r];
+#pragma unroll
+            for (int k = 0; k < NF; ++k)
+#pragma unroll
+                for (int ch = 0; ch < NC; ++ch) v[k][ch] = LoadF<TI>::get(rowp + coff[k] + ch * (int)sizeof(TI));
+            const float ry = ry0 + (float)r;
+            const float ur = -ry * g.sn, vr = ry * g.cs;
+#pragma unroll
+            for (int k = 0; k < NF; ++k) {
+                const float rx = rx0 + (float)k;
+                const float mu = g.half - fabsf(fmaf(rx, g.cs, ur));
+                const float mv = g.half - fabsf(fmaf(rx, g.sn, vr));
+                const float m = fminf(mu, mv);
+                worst = fminf(worst, fabsf(m));
+                if (m >= 0.0f) {  // closed point-in-square (837-864); predicated adds, no branch
+                    count += 1.0f;
+#pragma unroll
+                    for (int ch = 0; ch < NC; ++ch) acc[ch] += v[k][ch];
+                }
+            }
+        }
+    }
+    if (!inside_img || worst < tau) {  // border pixel, or a centre within the guard band of a footprint edge: FP64 decides
+        int c64;
+        double a64[NC];
+        pixel_fast_f64<TI, NC>(kp, x, y, c64, a64);
+#pragma unroll
+        for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, c64 > 0 ? a64[ch] / (double)c64 : 0.0);
+    } else {
+        const float inv = count > 0.0f ? 1.0f / count : 0.0f;
+#pragma unroll
+        for (int ch = 0; ch < NC; ++ch) store_f<TO>(drow, x * NC + ch, acc[ch] * inv);
+    }
+}
+
+template <typename TI, typename TO, int NC>
+cudaError_t launch_fast3(const AaiKernelParams &kp, cudaStream_t stream) {
+    const int rows = kp.row1 - kp.row0;
+    if (rows <= 0 || kp.dst_w <= 0) return cudaSuccess;
+    dim3 block(TILE_W, TILE_H);
+    dim3 grid((kp.dst_w + TILE_W - 1) / TILE_W, (rows + TILE_H - 1) / TILE_H, kp.batch > 1 ? kp.batch : 1);
+    if (kp.scale == 1 && kp.quadrant == 0)
+        fast_kernel_f32u<TI, TO, NC, true><<<grid, block, 0, stream>>>(kp);
+    else
+        fast_kernel_f32u<TI, TO, NC, false><<<grid, block, 0, stream>>>(kp);
+    return cudaGetLastError();
+}
+template <typename TI>
+cudaError_t launch_fast1(const AaiKernelParams &kp, int dst_dtype, cudaStream_t stream) {
+    const bool one = kp.channels == 1;
+    switch (dst_dtype) {  // (double destinations take the FP64 fast kernel)
+        case AAI_F32: return one ? launch_fast3<TI, float, 1>(kp, stream) : launch_fast3<TI, float, 3>(kp, stream);
+        case AAI_U8: return one ? launch_fast3<TI, uint8_t, 1>(kp, stream) : launch_fast3<TI, uint8_t, 3>(kp, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 }  // namespace
 
 #define AAI_CAT2(a, b) a##b
@@ -455,6 +539,16 @@ int AAI_CAT(aai_launch_overlap_f32_n, AAI_MAXN)(const AaiKernelParams &kp, int s
         case AAI_F64: return (int)launch1<double>(kp, dst_dtype, st);
         case AAI_F32: return (int)launch1<float>(kp, dst_dtype, st);
         case AAI_U8: return (int)launch1<uint8_t>(kp, dst_dtype, st);
+        default: return (int)cudaErrorInvalidValue;
+    }
+}
+
+// fast mode, FP32 arithmetic: float / 8-bit sources and destinations, 1 or 3 channels
+int AAI_CAT(aai_launch_fast_f32_n, AAI_MAXN)(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (src_dtype) {
+        case AAI_F32: return (int)launch_fast1<float>(kp, dst_dtype, st);
+        case AAI_U8: return (int)launch_fast1<uint8_t>(kp, dst_dtype, st);
         default: return (int)cudaErrorInvalidValue;
     }
 }

@@ -15,6 +15,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", type=int, default=4)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--arith", default="f64")
+ap.add_argument("--mode", type=int, default=1, help="1 area average, 2 fast mode")
+ap.add_argument("--dst", default="same", help="canvas element type: same (as the source) | float32")
 ap.add_argument("--lib", default="", help="another build of libaai_b200.so (A/B variants)")
 ap.add_argument("--batch", type=int, default=0, help="config 5: slices per launch (aai_run_device_batch)")
 args = ap.parse_args()
@@ -28,7 +30,7 @@ if cfg["dtype"] == "uint8":
     src = torch.randint(0, 256, (cfg["h"], cfg["w"]) + tail, dtype=torch.uint8, device=dev)
 else:
     src = torch.rand((cfg["h"], cfg["w"]) + tail, dtype=torch.float32, device=dev) * 4096
-dst = torch.empty((plan.dst_h, plan.dst_w) + tail, dtype=torch.float32, device=dev)
+dst = torch.empty((plan.dst_h, plan.dst_w) + tail, dtype=src.dtype if args.dst == "same" else torch.float32, device=dev)
 si, di = aai.tensor_image(src), aai.tensor_image(dst)
 arith = aai.ARITH_F32 if args.arith == "f32" else aai.ARITH_F64
 st = torch.cuda.current_stream().cuda_stream
@@ -43,7 +45,8 @@ if args.batch:
 
     aai_run = run_device
 else:
-    aai_run = aai.run_device
+    def aai_run(plan, si, di, arith, stream):
+        aai.run_device(plan, si, di, mode=args.mode, arith=arith, stream=stream)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 aai_run(plan, si, di, arith=arith, stream=st)
 torch.cuda.synchronize()
