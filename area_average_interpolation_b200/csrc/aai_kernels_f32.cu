@@ -84,8 +84,9 @@ __device__ __forceinline__ void store_f<uint8_t>(void *row, int idx, float v) {
 //   ADDR_GENERAL  expanded + quadrant-rotated frame, separable byte offset col_off(i) + row_off(j)
 //   ADDR_IDENT    scale 1, quadrant 0: expanded pixel (i,j) IS source pixel (i,j), offsets fold into the loads
 //   ADDR_GROUPED  general frame with scale >= MAXN-1 (upscaling): the <= MAXN x MAXN cells of a footprint fall into at
-//                 most 2 x 2 source pixels, so the areas (and the quirk corrections) are summed per source pixel in
-//                 four registers and each source pixel is loaded ONCE per canvas pixel instead of once per cell
+//                 most 2 x 2 source pixels, so the four weights are computed DIRECTLY (aai_quadrant_areas_f32: Green form
+//                 about the corner of the source-pixel boundaries, no loop over cells), the quirk corrections are added
+//                 per source pixel, and each source pixel is loaded ONCE per canvas pixel
 enum { ADDR_GENERAL = 0, ADDR_IDENT = 1, ADDR_GROUPED = 2 };
 template <typename TI, typename TO, int NC, int ADDR>
 __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
@@ -126,19 +127,21 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         const int dj0 = jy0 - iry;
         const float rx0 = (float)(ix0 - irx) - fx;
         float yt[MAXN + 1], yb[MAXN + 1];
+        if (!GROUPED) {
 #pragma unroll
-        for (int k = 0; k + 1 <= MAXN; k += 2) {  // two grid lines per packed instruction
-            AaiF2 t2, b2;
-            aai_chord_v_f32x2(g, aai_f2(rx0 + ((float)k - 0.5f), rx0 + ((float)k + 0.5f)), t2, b2);
-            yt[k] = t2.x;
-            yt[k + 1] = t2.y;
-            yb[k] = b2.x;
-            yb[k + 1] = b2.y;
+            for (int k = 0; k + 1 <= MAXN; k += 2) {  // two grid lines per packed instruction
+                AaiF2 t2, b2;
+                aai_chord_v_f32x2(g, aai_f2(rx0 + ((float)k - 0.5f), rx0 + ((float)k + 0.5f)), t2, b2);
+                yt[k] = t2.x;
+                yt[k + 1] = t2.y;
+                yb[k] = b2.x;
+                yb[k + 1] = b2.y;
+            }
+            if ((MAXN + 1) & 1) aai_chord_v_f32(g, rx0 + ((float)MAXN - 0.5f), yt[MAXN], yb[MAXN]);
         }
-        if ((MAXN + 1) & 1) aai_chord_v_f32(g, rx0 + ((float)MAXN - 0.5f), yt[MAXN], yb[MAXN]);
-        float xlT, xrT;  // chord of the footprint on the row's top grid line
+        float xlT = 0.0f, xrT = 0.0f;  // chord of the footprint on the row's top grid line
         const float t0 = ((float)dj0 - fy) - 0.5f;  // top of row 0
-        aai_chord_h_f32(g, t0, xlT, xrT);
+        if (!GROUPED) aai_chord_h_f32(g, t0, xlT, xrT);
         const float e0 = rx0 - 0.5f;  // left boundary of column 0
         constexpr int ESZ = (int)sizeof(TI) * NC;
         const char *rowp0 = (const char *)kp.src + (int64_t)(jy0 - src_row0(kp)) * kp.src_pitch + (int64_t)ix0 * ESZ;
@@ -163,26 +166,32 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
 #pragma unroll
             for (int k = 0; k < MAXN; ++k) coff[k] = col_off(ix0 + min(k, ncols - 1));
         }
-        // GROUPED: column k belongs to the first source column (group A, bit k of colA) or to the second one (group B);
-        // rows likewise (rowTop); W[row group][column group] = total weight of the source pixel.  Along an axis the
+        // GROUPED: the first nA columns of the cell range belong to the first source column, the rest to the second one;
+        // rows likewise (nT); W[row group][column group] = total weight of the source pixel.  Along an axis the
         // expanded coordinate e moves by +-1 per cell, so the first group holds S - e mod S (resp. e mod S + 1) cells.
-        unsigned colA = 0, rowTop = 0;
+        int nA = MAXN, nT = MAXN;
         float W00 = 0.0f, W01 = 0.0f, W10 = 0.0f, W11 = 0.0f;
         if (GROUPED) {
-            auto first_group = [&](int e, int step) -> unsigned {  // mask of the cells sharing the first cell's source
+            auto first_group = [&](int e, int step) -> int {  // cells sharing the first cell's source pixel
                 const int rem = e - (int)div_s(e) * kp.scale;
-                const int n = step > 0 ? kp.scale - rem : rem + 1;
-                return n >= MAXN ? (1u << MAXN) - 1u : (1u << n) - 1u;
+                return step > 0 ? kp.scale - rem : rem + 1;
             };
             const int ac = swapped ? kp.e_ayi : kp.e_axi, ec0 = swapped ? kp.e_ay0 : kp.e_ax0;
             const int ar = swapped ? kp.e_axj : kp.e_ayj, er0 = swapped ? kp.e_ax0 : kp.e_ay0;
-            colA = first_group(ac * ix0 + ec0, ac);
-            rowTop = first_group(ar * jy0 + er0, ar);
+            nA = first_group(ac * ix0 + ec0, ac);
+            nT = first_group(ar * jy0 + er0, ar);
+            // the source-pixel boundaries inside the cell range (at most one per axis: the range holds <= scale + 1
+            // cells), relative to the footprint centre; none -> beyond the footprint
+            const float tX = nA < ncols ? e0 + (float)nA : g.q_far;
+            const float tY = nT < nrows ? t0 + (float)nT : g.q_far;
+            aai_quadrant_areas_f32(g, tX, tY, W00, W01, W10, W11);
         }
         // lengths of the cells' top sides inside the footprint: the previous row's bottom sides
         float lenTop[MAXN];
+        if (!GROUPED) {
 #pragma unroll
-        for (int k = 0; k < MAXN; ++k) lenTop[k] = aai_overlap1_f32(xlT, xrT, e0 + (float)k);
+            for (int k = 0; k < MAXN; ++k) lenTop[k] = aai_overlap1_f32(xlT, xrT, e0 + (float)k);
+        }
         // Source values are fetched one row ahead of their use (the loads of row r+1 are in flight while the areas of
         // row r are computed): the accumulate at the end of a row never waits for its own row's loads.
         // (Single-channel kernels only: three channels would need 30 staging registers.)
@@ -209,11 +218,9 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         auto row = [&](int r, float (&cur)[MAXN][NC], float (&nxt)[MAXN][NC]) {
             if (PREFETCH) {
                 if (r + 1 < nrows) fetch(r + 1, nxt);
-            } else if (!GROUPED) {
+            } else {
                 rowp = IDENT ? rowp0 + (int64_t)r * kp.src_pitch : (const char *)kp.src + row_off(jy0 + r);
             }
-            float rowA = 0.0f, rowB = 0.0f;  // GROUPED: this row's area in the first / second source column
-            const bool top = (rowTop >> r) & 1u;
             const float ry = (float)(dj0 + r) - fy;
             float xlB, xrB;
             aai_chord_h_f32(g, ry + 0.5f, xlB, xrB);
@@ -221,12 +228,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             float lenL = aai_overlap1_f32(yt[0], yb[0], ey);
             const float ur = -ry * g.sn, vr = ry * g.cs;
             auto take = [&](int k, float area) {
-                if (GROUPED) {  // cells beyond ncols have area exactly 0
-                    if ((colA >> k) & 1u)
-                        rowA += area;
-                    else
-                        rowB += area;
-                } else if (PREFETCH) {
+                if (PREFETCH) {
 #pragma unroll
                     for (int ch = 0; ch < NC; ++ch) acc[ch] = fmaf(cur[k][ch], area, acc[ch]);
                 } else if (k < MINC || k < ncols) {  // load at the point of use
@@ -269,22 +271,18 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 const float area = aai_cell_exact_f32(g, u0, v0, lenT, lenB, lenL, lenR);
                 take(k, area);
             }
-            if (GROUPED) {
-                W00 += top ? rowA : 0.0f;
-                W01 += top ? rowB : 0.0f;
-                W10 += top ? 0.0f : rowA;
-                W11 += top ? 0.0f : rowB;
-            }
         };
+        if (!GROUPED) {
 #pragma unroll kRowUnroll
-        for (int r = 0; r < nrows; ++r) {
-            float nxt[MAXN][NC];
-            row(r, buf, nxt);
-            if (PREFETCH) {
+            for (int r = 0; r < nrows; ++r) {
+                float nxt[MAXN][NC];
+                row(r, buf, nxt);
+                if (PREFETCH) {
 #pragma unroll
-                for (int k = 0; k < MAXN; ++k)
+                    for (int k = 0; k < MAXN; ++k)
 #pragma unroll
-                    for (int ch = 0; ch < NC; ++ch) buf[k][ch] = nxt[k][ch];
+                        for (int ch = 0; ch < NC; ++ch) buf[k][ch] = nxt[k][ch];
+                }
             }
         }
         // Total overlap: the exact areas of a footprint inside the image add up to L^2 (border pixels never get here).
@@ -302,18 +300,25 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 Mi = max(0, min(Mi, Mlim));
                 const int k = g.steep ? mi : Mi, r = g.steep ? Mi : mi;
                 if (GROUPED) {  // corrections go to the weights of the cells' source pixels: no loads here
-                    // (group membership as 0/1 factors: four FMAs instead of four selects + four adds)
-                    auto add_w = [&](int kk, int rr, float d) {
-                        const float a = (float)((colA >> kk) & 1u), t = (float)((rowTop >> rr) & 1u);
-                        const float at = a * t, ab = a - at, bt = t - at;
-                        W00 = fmaf(at, d, W00);
-                        W01 = fmaf(bt, d, W01);
-                        W10 = fmaf(ab, d, W10);
-                        W11 = fmaf((1.0f - a) - bt, d, W11);
-                    };
-                    add_w(k, r, d_before);
-                    add_w(k + (g.steep ? 1 : 0), r + (g.steep ? 0 : 1), d_after);
-                    sumA += d_before + d_after;
+                    // the two cells are neighbours along the minor axis and share the major index
+                    const int k1 = k + (g.steep ? 1 : 0), r1 = r + (g.steep ? 0 : 1);
+                    const float both = d_before + d_after;
+                    if (g.steep) {  // same row: split by column group, then one row group
+                        const float dA = (k < nA ? d_before : 0.0f) + (k1 < nA ? d_after : 0.0f), dB = both - dA;
+                        const bool top = r < nT;
+                        W00 += top ? dA : 0.0f;
+                        W01 += top ? dB : 0.0f;
+                        W10 += top ? 0.0f : dA;
+                        W11 += top ? 0.0f : dB;
+                    } else {  // same column: split by row group, then one column group
+                        const float dT = (r < nT ? d_before : 0.0f) + (r1 < nT ? d_after : 0.0f), dBt = both - dT;
+                        const bool left = k < nA;
+                        W00 += left ? dT : 0.0f;
+                        W10 += left ? dBt : 0.0f;
+                        W01 += left ? 0.0f : dT;
+                        W11 += left ? 0.0f : dBt;
+                    }
+                    sumA += both;
                     return;
                 }
                 const char *p0, *p1;

@@ -261,3 +261,46 @@ extern "C" void aai_test_footprint_edges_f64(double c, double s, double L, doubl
     }
     *total = sum;
 }
+
+// Quadrant weights of the upscaling path (aai_quadrant_areas_f32) against the sum of the exact per-cell areas (FP64
+// Green form, quirk off) of the cells on each side of the source-pixel boundaries.  (cx, cy): footprint centre in the
+// expanded frame; boundaries at multiples of S minus 1/2.  out[k] = {W00, W01, W10, W11, R00, R01, R10, R11}.
+extern "C" void aai_test_quadrant_areas(double c, double s, double L, int S, const double *cx, const double *cy,
+                                        double *out, long long n) {
+    const AaiShape g = make_shape(c, s, L);
+    const AaiShapeF gf = make_shape_f(c, s, L);
+    const double ext = g.half * (c + s) + 0.5 + 1e-9;
+    for (long long k = 0; k < n; ++k) {
+        const int ix0 = (int)std::ceil(cx[k] - ext), ix1 = (int)std::floor(cx[k] + ext);
+        const int jy0 = (int)std::ceil(cy[k] - ext), jy1 = (int)std::floor(cy[k] + ext);
+        // first boundary to the right of cell ix0: after the cell i with (i + 1) % S == 0
+        auto boundary = [&](int i0, int i1) -> double {  // coordinate of the boundary inside [i0, i1], or +1e6
+            for (int i = i0; i < i1; ++i)
+                if (((i + 1) % S + S) % S == 0) return (double)i + 0.5;
+            return 1e6;
+        };
+        const double X = boundary(ix0, ix1), Y = boundary(jy0, jy1);
+        const double irx = std::nearbyint(cx[k]), iry = std::nearbyint(cy[k]);
+        const float fx = (float)(cx[k] - irx), fy = (float)(cy[k] - iry);
+        const float tX = X > 1e5 ? gf.q_far : (float)(X - irx) - fx, tY = Y > 1e5 ? gf.q_far : (float)(Y - iry) - fy;
+        float w[4];
+        aai_quadrant_areas_f32(gf, tX, tY, w[0], w[1], w[2], w[3]);
+        double r[4] = {0, 0, 0, 0};
+        for (int j = jy0; j <= jy1; ++j)
+            for (int i = ix0; i <= ix1; ++i) {
+                const double rx = i - cx[k], ry = j - cy[k];
+                double xlT, xrT, xlB, xrB, ytL, ybL, ytR, ybR;
+                aai_chord_h(g, ry - 0.5, xlT, xrT);
+                aai_chord_h(g, ry + 0.5, xlB, xrB);
+                aai_chord_v(g, rx - 0.5, ytL, ybL);
+                aai_chord_v(g, rx + 0.5, ytR, ybR);
+                const double a = aai_cell_area(g, rx, ry, aai_overlap1(xlT, xrT, rx), aai_overlap1(xlB, xrB, rx),
+                                               aai_overlap1(ytL, ybL, ry), aai_overlap1(ytR, ybR, ry), false);
+                r[(j > Y ? 2 : 0) + (i > X ? 1 : 0)] += a;
+            }
+        for (int q = 0; q < 4; ++q) {
+            out[8 * k + q] = w[q];
+            out[8 * k + 4 + q] = r[q];
+        }
+    }
+}

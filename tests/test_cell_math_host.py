@@ -28,6 +28,7 @@ def cellmath(built):
     lib.aai_test_footprint_edges_f64.argtypes = [C.c_double] * 5 + [C.c_int] * 3 + [C.c_void_p] * 2
     lib.aai_test_edge_pair_vs_scalar.argtypes = [C.c_double] * 3 + [C.c_void_p] * 2 + [C.c_longlong]
     lib.aai_test_edge_pair_vs_scalar.restype = C.c_longlong
+    lib.aai_test_quadrant_areas.argtypes = [C.c_double] * 3 + [C.c_int] + [C.c_void_p] * 3 + [C.c_longlong]
     lib.aai_test_pair_areas_f32x2.argtypes = [C.c_double] * 3 + [C.c_void_p] * 7 + [C.c_longlong]
     return lib
 
@@ -287,3 +288,28 @@ def test_fp64_edge_formulation_matches_the_per_cell_form(cellmath, theta, side):
         if np.abs(got - want).max() > 1e-12 * amp or abs(total[0] - want.sum()) > 1e-11 * amp:
             bad += 1
     assert bad == 0
+
+
+@pytest.mark.parametrize("ratio,theta", [(1.7, 45.0), (1.7, 10.0), (1.7, 80.0), (1.5, 33.0), (2.0, 61.0), (2.8, 45.0),
+                                          (2.3, 17.3), (1.42, 45.0)])
+def test_quadrant_weights_equal_the_sum_of_exact_cell_areas(cellmath, ratio, theta):
+    """Upscaling path of the FP32 kernel: the four source-pixel weights computed directly (Green form about the corner
+    of the source-pixel boundaries) equal the per-source-pixel sums of the exact cell areas; they add up to L^2."""
+    S = int(ratio * np.sqrt(2.0) + 1 + 2.2e-16)
+    L = S / ratio
+    assert S >= 3
+    t = np.deg2rad(theta)
+    c, s = np.cos(t), np.sin(t)
+    rng = np.random.default_rng(int(ratio * 1000 + theta))
+    n = 40000
+    cx = rng.uniform(10.0, 10.0 + 3 * S, size=n)
+    cy = rng.uniform(10.0, 10.0 + 3 * S, size=n)
+    # include centres on / next to the boundaries and lattice points
+    cx[:200] = np.round(cx[:200] * 2) / 2
+    cy[100:300] = np.round(cy[100:300] * 2) / 2
+    out = np.zeros((n, 8))
+    cellmath.aai_test_quadrant_areas(c, s, L, S, cx.ctypes.data, cy.ctypes.data, out.ctypes.data, n)
+    w, r = out[:, :4], out[:, 4:]
+    assert np.abs(r.sum(axis=1) - L * L).max() < 1e-9  # the checker itself: exact areas tile the footprint
+    assert np.abs(w - r).max() < 4e-6 * L * L, float(np.abs(w - r).max())
+    assert (r > 1e-3).sum(axis=1).max() == 4 and (r > 1e-3).sum(axis=1).min() == 1  # all quadrant patterns occur
