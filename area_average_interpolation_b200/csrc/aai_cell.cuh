@@ -182,7 +182,6 @@ struct AaiShapeF {
     float kq_s, kq_c;  // 1/(s L), 1/(c L)
     float qq_cs, qq_sc;  // c/(2 s), s/(2 c)
     float half_side;   // L/2
-    float q_far;       // a boundary coordinate beyond the footprint ("no boundary"): small, so that nothing cancels
     int steep;   // 1: sin <= cos (major axis = y, the edges cross vertical grid lines rarely)
     int ncross;  // floor(L min(s,c)) + 1: most minor-axis grid lines one left/right edge can cross
 };
@@ -223,7 +222,6 @@ inline AaiShapeF aai_make_shape_f(double c, double s, double L) {
     g.qq_cs = (float)(c / (2.0 * s));
     g.qq_sc = (float)(s / (2.0 * c));
     g.half_side = (float)(L / 2);
-    g.q_far = (float)(L + 1.0);
     g.steep = s <= c ? 1 : 0;
     g.ncross = (int)floor(L * mn) + 1;
     return g;
@@ -318,8 +316,8 @@ AAI_HD AaiF2 aai_cell_exact_f32x2(const AaiShapeF &g, AaiF2 u0, AaiF2 v0, AaiF2 
 // ------------------------------------------------------------------------------------------------------------
 // Upscaling (expansion S >= 3, footprint narrower than one source pixel + 1 cell): the <= 4 x 4 expanded cells a
 // footprint touches are replicas of at most 2 x 2 source pixels, separated by ONE vertical source-pixel boundary
-// x = Cx + tX and ONE horizontal one y = Cy + tY (coordinates relative to the footprint centre; g.q_far when the
-// boundary does not cross the footprint: every cell then lies on its near side).  The exact cell areas of Source.cpp:1052-1401 add up, per source pixel, to
+// x = Cx + tX and ONE horizontal one y = Cy + tY (coordinates relative to the footprint centre; hasX / hasY false
+// when there is no such boundary inside the cell range: every cell then lies on its near side).  The exact cell areas of Source.cpp:1052-1401 add up, per source pixel, to
 // the area of the footprint inside that pixel's quadrant, so the four weights are computed directly instead of cell
 // by cell: Green's theorem about the corner P = (tX, tY) --
 //     area(footprint ∩ quadrant) = 1/2 sum over the 4 footprint edges of  dist(P, edge line) * |edge ∩ quadrant|
@@ -330,17 +328,19 @@ AAI_HD AaiF2 aai_cell_exact_f32x2(const AaiShapeF &g, AaiF2 u0, AaiF2 v0, AaiF2 
 // The four weights add up to L^2.  (The reference's shape-2/4 quirk is applied on top, per edge crossing, as in the
 // general path.)
 // ------------------------------------------------------------------------------------------------------------
-AAI_HD void aai_quadrant_areas_f32(const AaiShapeF &g, float tX, float tY, float &W00, float &W01, float &W10,
-                                   float &W11) {
+AAI_HD void aai_quadrant_areas_f32(const AaiShapeF &g, float tX, float tY, bool hasX, bool hasY, float &W00,
+                                   float &W01, float &W10, float &W11) {
+    // A boundary that does not cross the footprint puts every cell on its near side (x < tX resp. y < tY always true);
+    // P then sits on the footprint's centre line, so that the signed distances stay O(L) and nothing cancels.
+    const float px = hasX ? tX : 0.0f, py = hasY ? tY : 0.0f;
     // footprint-local coordinates of P and its signed distances to the four edge lines (positive inside), times L/2
-    const float uP = fmaf(tX, g.cs, -tY * g.sn), vP = fmaf(tX, g.sn, tY * g.cs);
+    const float uP = fmaf(px, g.cs, -py * g.sn), vP = fmaf(px, g.sn, py * g.cs);
     const float D1 = (g.half - uP) * g.half_side, D2 = (g.half + uP) * g.half_side;  // edges u = +h, u = -h
     const float D3 = (g.half - vP) * g.half_side, D4 = (g.half + vP) * g.half_side;  // edges v = +h, v = -h
-    const float ax = tX * g.kq_s, bx = tX * g.kq_c, ay = tY * g.kq_s, by = tY * g.kq_c;
     // u = +-h (direction (s, c): x and y both grow with the parameter): x < tX <=> t < a, y < tY <=> t < b
     {
-        const float a1 = aai_sat(ax + (0.5f - g.qq_cs)), b1 = aai_sat(by + (0.5f + g.qq_sc));
-        const float a2 = aai_sat(ax + (0.5f + g.qq_cs)), b2 = aai_sat(by + (0.5f - g.qq_sc));
+        const float a1 = hasX ? aai_sat(fmaf(px, g.kq_s, 0.5f - g.qq_cs)) : 1.0f, b1 = hasY ? aai_sat(fmaf(py, g.kq_c, 0.5f + g.qq_sc)) : 1.0f;
+        const float a2 = hasX ? aai_sat(fmaf(px, g.kq_s, 0.5f + g.qq_cs)) : 1.0f, b2 = hasY ? aai_sat(fmaf(py, g.kq_c, 0.5f - g.qq_sc)) : 1.0f;
         const float lo1 = fminf(a1, b1), hi1 = fmaxf(a1, b1), lo2 = fminf(a2, b2), hi2 = fmaxf(a2, b2);
         W00 = fmaf(D1, lo1, D2 * lo2);
         W11 = fmaf(D1, 1.0f - hi1, D2 * (1.0f - hi2));
@@ -351,8 +351,8 @@ AAI_HD void aai_quadrant_areas_f32(const AaiShapeF &g, float tX, float tY, float
     }
     // v = +-h (direction (c, -s): x grows, y falls with the parameter): x < tX <=> t < a, y < tY <=> t > b
     {
-        const float a3 = aai_sat(bx + (0.5f - g.qq_sc)), b3 = aai_sat((0.5f + g.qq_cs) - ay);
-        const float a4 = aai_sat(bx + (0.5f + g.qq_sc)), b4 = aai_sat((0.5f - g.qq_cs) - ay);
+        const float a3 = hasX ? aai_sat(fmaf(px, g.kq_c, 0.5f - g.qq_sc)) : 1.0f, b3 = hasY ? aai_sat(fmaf(-py, g.kq_s, 0.5f + g.qq_cs)) : 0.0f;
+        const float a4 = hasX ? aai_sat(fmaf(px, g.kq_c, 0.5f + g.qq_sc)) : 1.0f, b4 = hasY ? aai_sat(fmaf(-py, g.kq_s, 0.5f - g.qq_cs)) : 0.0f;
         const float lo3 = fminf(a3, b3), hi3 = fmaxf(a3, b3), lo4 = fminf(a4, b4), hi4 = fmaxf(a4, b4);
         W10 += fmaf(D3, lo3, D4 * lo4);
         W01 += fmaf(D3, 1.0f - hi3, D4 * (1.0f - hi4));

@@ -18,6 +18,10 @@
 //     the smallest decision margin of the pixel is tracked and, when it falls inside the FP32 guard band, or when
 //     the image border clips the footprint (border pixels need relative accuracy), the pixel is redone in FP64
 //     (pixel_f64) -- FP32 rounding can never flip one of the reference's discontinuous decisions.
+#include <cuda.h>
+
+#include <cmath>
+
 #include "aai_device.cuh"
 
 #ifndef AAI_MAXN
@@ -72,6 +76,132 @@ __device__ __forceinline__ void store_f<uint8_t>(void *row, int idx, float v) {
     ((uint8_t *)row)[idx] = (uint8_t)__float2int_rd(fminf(fmaxf(v + 0.5f, 0.0f), 255.0f));  // round half up, saturate
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// STAGED variants (the north star's lay-out): the source window of a CTA's 16 x 8 canvas pixels is brought into shared
+// memory by ONE 2-D TMA tile load (cp.async.bulk.tensor.2d through a CUtensorMap, completion on an mbarrier) and the
+// cells are read with LDS instead of LDG.  Footprints of a rotated canvas row step through the source diagonally, so a
+// warp's 32 loads of "cell k" hit ~28 different 32-byte sectors -- 28 L1 tag wavefronts per LDG -- while the same 32
+// addresses in shared memory cost ~3 bank-conflict wavefronts.  Fast mode (16 loads and ~9 other instructions per cell)
+// is limited by exactly that; the overlap kernel (135 instructions per row of 5 cells) is not.
+// Identity addressing only (scale 1, quadrant 0); the window origin is rounded down to a 16-byte boundary (TMA
+// requirement); out-of-image parts of the box are zero-filled by the hardware and never read (pixels whose footprint
+// box leaves the image take the FP64 path, which reads global memory).
+// ------------------------------------------------------------------------------------------------------------
+struct StageParams {
+    int bw, bh;  // TMA box = source window of one CTA: elements (pixels x channels) per row, rows
+};
+
+__device__ __forceinline__ uint32_t st_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Loads the CTA's source window; every thread of the CTA must call it (it synchronises).  Returns the window origin
+// (sox in ELEMENTS of the interleaved row, soy in rows of the whole image) -- valid also when nothing was loaded
+// because the window misses the image.
+template <int EB, int NC>  // EB = bytes per element, NC = interleaved channels
+__device__ __forceinline__ void stage_window(const CUtensorMap *tmap, const AaiKernelParams &kp, const StageParams &sp,
+                                             unsigned char *smem, uint64_t *bar, float ext, int &sox, int &soy) {
+    const int x0 = blockIdx.x * TILE_W, y0 = kp.row0 + blockIdx.y * TILE_H;
+    double lox = 1e300, loy = 1e300;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {  // the centre map is affine: the extremes sit at the tile's corners
+        const double xx = (double)(x0 + (c & 1) * (TILE_W - 1)), yy = (double)(y0 + (c >> 1) * (TILE_H - 1));
+        lox = fmin(lox, fma(xx, kp.aff_xx, fma(yy, kp.aff_xy, kp.aff_x0)));
+        loy = fmin(loy, fma(xx, kp.aff_yx, fma(yy, kp.aff_yy, kp.aff_y0)));
+    }
+    constexpr int EAL = 16 / EB;  // elements per 16 bytes: the TMA start coordinate must be a multiple of it
+    int ex = (__double2int_rd(lox - (double)ext) - 1) * NC;
+    ex = (ex >= 0 ? ex / EAL : -((-ex + EAL - 1) / EAL)) * EAL;
+    sox = ex;
+    soy = __double2int_rd(loy - (double)ext) - 1;
+    const int tid = threadIdx.y * TILE_W + threadIdx.x;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)(sp.bw * sp.bh * EB);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(st_smem_u32(bar)), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+                "r"(st_smem_u32(smem)),
+            "l"(tmap), "r"(st_smem_u32(bar)), "r"(sox), "r"(soy - src_row0(kp))
+            : "memory");
+    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "ST_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni ST_DONE;\n"
+        "bra.uni ST_WAIT;\n"
+        "ST_DONE:\n"
+        "}\n" ::"r"(st_smem_u32(bar)),
+        "r"(0)
+        : "memory");
+}
+
+template <typename TI, bool STAGED>
+struct LoadS {
+    static __device__ __forceinline__ float get(const char *p) {
+        if constexpr (STAGED)
+            return (float)*reinterpret_cast<const TI *>(p);  // shared memory (the pointer derives from the staged tile)
+        else
+            return LoadF<TI>::get(p);
+    }
+};
+
+// ---- host side of the staged variants: tensor map over the (band of the / stack of) source image(s) + box size ------
+typedef CUresult (*StEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+StEncodeTiledFn st_encode_fn() {
+    static const StEncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            return (StEncodeTiledFn)p;
+        cudaGetLastError();
+        return (StEncodeTiledFn) nullptr;
+    }();
+    return fn;
+}
+
+struct StageHost {
+    CUtensorMap map;
+    StageParams sp;
+    size_t smem;
+};
+// false: the staged variant does not apply (the caller launches the LDG kernel)
+template <typename TI, int NC>
+bool stage_prepare(const AaiKernelParams &kp, double ext, StageHost &h) {
+    StEncodeTiledFn enc = st_encode_fn();
+    if (!enc || kp.scale != 1 || kp.quadrant != 0 || sizeof(TI) == 8) return false;
+    if ((kp.src_pitch % 16) != 0 || (reinterpret_cast<uintptr_t>(kp.src) % 16) != 0) return false;
+    constexpr int EB = (int)sizeof(TI), EAL = 16 / EB;
+    // extent of the footprint centres over one tile (the centre map is affine), plus the cell range on both sides, plus
+    // the slack of stage_window() (one pixel, alignment of the origin)
+    const double sx = (TILE_W - 1) * std::fabs(kp.aff_xx) + (TILE_H - 1) * std::fabs(kp.aff_xy);
+    const double sy = (TILE_W - 1) * std::fabs(kp.aff_yx) + (TILE_H - 1) * std::fabs(kp.aff_yy);
+    const int wpx = (int)std::ceil(sx + 2.0 * ext) + 4;
+    h.sp.bw = (wpx * NC + (EAL - 1) + EAL - 1) / EAL * EAL;
+    h.sp.bh = (int)std::ceil(sy + 2.0 * ext) + 4;
+    h.smem = (size_t)h.sp.bw * h.sp.bh * EB;
+    if (h.sp.bw > 256 || h.sp.bh > 256 || h.smem > 30 * 1024) return false;
+    // one tall 2-D tensor: a stack of equally strided slices is addressed through its row index (src_batch_rows)
+    const int64_t rows = kp.batch > 1 ? (int64_t)kp.src_batch_rows * kp.batch : (int64_t)kp.src_rows;
+    const cuuint64_t gdim[2] = {(cuuint64_t)kp.src_w * NC, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)kp.src_pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)h.sp.bw, (cuuint32_t)h.sp.bh};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = EB == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    return enc(&h.map, dt, 2, const_cast<void *>(kp.src), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+
 // IDENT: scale 1, quadrant 0 (expanded pixel (i,j) IS source pixel (i,j)): constant element stride, offsets fold
 // into the load instruction.  Otherwise the general expanded-frame affine map + division by the scale.
 #ifndef AAI_F32_MIN_BLOCKS
@@ -88,10 +218,11 @@ __device__ __forceinline__ void store_f<uint8_t>(void *row, int idx, float v) {
 //                 about the corner of the source-pixel boundaries, no loop over cells), the quirk corrections are added
 //                 per source pixel, and each source pixel is loaded ONCE per canvas pixel
 enum { ADDR_GENERAL = 0, ADDR_IDENT = 1, ADDR_GROUPED = 2 };
-template <typename TI, typename TO, int NC, int ADDR>
-__global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
-    overlap_kernel_f32(const __grid_constant__ AaiKernelParams kp) {
+// stage / spitch / sox / soy: the CTA's staged source window (STAGED only): row pitch in bytes, origin in elements / rows
+template <typename TI, typename TO, int NC, int ADDR, bool STAGED>
+__device__ __forceinline__ void overlap_body(const AaiKernelParams &kp, const char *stage, int spitch, int sox, int soy) {
     constexpr bool IDENT = ADDR == ADDR_IDENT, GROUPED = ADDR == ADDR_GROUPED;
+    static_assert(!STAGED || IDENT, "staging is implemented for identity addressing");
     const int x = blockIdx.x * TILE_W + threadIdx.x;
     const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
     if (x >= kp.dst_w || y >= kp.row1) return;
@@ -144,7 +275,10 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         if (!GROUPED) aai_chord_h_f32(g, t0, xlT, xrT);
         const float e0 = rx0 - 0.5f;  // left boundary of column 0
         constexpr int ESZ = (int)sizeof(TI) * NC;
-        const char *rowp0 = (const char *)kp.src + (int64_t)(jy0 - src_row0(kp)) * kp.src_pitch + (int64_t)ix0 * ESZ;
+        // row pitch and first cell of the footprint: in the source image, or (STAGED) in the CTA's shared-memory window
+        const int64_t pitch = STAGED ? (int64_t)spitch : kp.src_pitch;
+        const char *rowp0 = STAGED ? stage + (jy0 - soy) * spitch + (ix0 * NC - sox) * (int)sizeof(TI)
+                                   : (const char *)kp.src + (int64_t)(jy0 - src_row0(kp)) * kp.src_pitch + (int64_t)ix0 * ESZ;
         const char *rowp = rowp0;
         // General path: expanded pixel (i,j) -> source pixel is separable (one source coordinate depends on the
         // column only, the other on the row only; which one is swapped for quadrants 1/3), so the byte offset is
@@ -182,9 +316,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             nT = first_group(ar * jy0 + er0, ar);
             // the source-pixel boundaries inside the cell range (at most one per axis: the range holds <= scale + 1
             // cells), relative to the footprint centre; none -> beyond the footprint
-            const float tX = nA < ncols ? e0 + (float)nA : g.q_far;
-            const float tY = nT < nrows ? t0 + (float)nT : g.q_far;
-            aai_quadrant_areas_f32(g, tX, tY, W00, W01, W10, W11);
+            aai_quadrant_areas_f32(g, e0 + (float)nA, t0 + (float)nT, nA < ncols, nT < nrows, W00, W01, W10, W11);
         }
         // lengths of the cells' top sides inside the footprint: the previous row's bottom sides
         float lenTop[MAXN];
@@ -199,7 +331,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
         float buf[MAXN][NC];
         auto fetch = [&](int r, float (&v)[MAXN][NC]) {
             if (IDENT)
-                rowp = rowp0 + (int64_t)r * kp.src_pitch;
+                rowp = rowp0 + (int64_t)r * pitch;
             else
                 rowp = (const char *)kp.src + row_off(jy0 + r);
 #pragma unroll
@@ -209,7 +341,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 if (k < MINC || k < ncols) {  // columns beyond the footprint box are never read (their area is exactly 0)
                     const char *p = IDENT ? rowp + k * ESZ : rowp + coff[k];
 #pragma unroll
-                    for (int ch = 0; ch < NC; ++ch) v[k][ch] = LoadF<TI>::get(p + ch * (int)sizeof(TI));
+                    for (int ch = 0; ch < NC; ++ch) v[k][ch] = LoadS<TI, STAGED>::get(p + ch * (int)sizeof(TI));
                 }
             }
         };
@@ -219,7 +351,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             if (PREFETCH) {
                 if (r + 1 < nrows) fetch(r + 1, nxt);
             } else {
-                rowp = IDENT ? rowp0 + (int64_t)r * kp.src_pitch : (const char *)kp.src + row_off(jy0 + r);
+                rowp = IDENT ? rowp0 + (int64_t)r * pitch : (const char *)kp.src + row_off(jy0 + r);
             }
             const float ry = (float)(dj0 + r) - fy;
             float xlB, xrB;
@@ -235,7 +367,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                     const char *p = IDENT ? rowp + k * ESZ : rowp + coff[k];
 #pragma unroll
                     for (int ch = 0; ch < NC; ++ch)
-                        acc[ch] = fmaf(LoadF<TI>::get(p + ch * (int)sizeof(TI)), area, acc[ch]);
+                        acc[ch] = fmaf(LoadS<TI, STAGED>::get(p + ch * (int)sizeof(TI)), area, acc[ch]);
                 }
             };
             // cells two at a time on the packed FP32 pipe (FFMA2/FMUL2/FADD2), a last odd cell on the scalar one
@@ -293,7 +425,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
             const float g0m = g.steep ? e0 : t0, g0M = g.steep ? t0 : e0;
             // the two cells of a crossing are neighbours along the minor axis: one address, one stride.  Branch-free: an
             // event that does not apply has d = 0 (its cells are clamped into the footprint's range and contribute 0).
-            const int64_t minor_stride = IDENT ? (g.steep ? (int64_t)ESZ : kp.src_pitch) : 0;
+            const int64_t minor_stride = IDENT ? (g.steep ? (int64_t)ESZ : pitch) : 0;
             auto fix2 = [&](int mi, int Mi, float d_before, float d_after) {
                 const int mlim = (g.steep ? ncols : nrows) - 2, Mlim = (g.steep ? nrows : ncols) - 1;
                 mi = max(0, min(mi, mlim));
@@ -323,7 +455,7 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 }
                 const char *p0, *p1;
                 if (IDENT) {
-                    p0 = rowp0 + (int64_t)r * kp.src_pitch + (int64_t)k * ESZ;
+                    p0 = rowp0 + (int64_t)r * pitch + (int64_t)k * ESZ;
                     p1 = p0 + minor_stride;
                 } else {
                     p0 = (const char *)kp.src + row_off(jy0 + r) + col_off(ix0 + k);
@@ -332,8 +464,8 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                 sumA += d_before + d_after;
 #pragma unroll
                 for (int ch = 0; ch < NC; ++ch) {
-                    acc[ch] = fmaf(LoadF<TI>::get(p0 + ch * (int)sizeof(TI)), d_before, acc[ch]);
-                    acc[ch] = fmaf(LoadF<TI>::get(p1 + ch * (int)sizeof(TI)), d_after, acc[ch]);
+                    acc[ch] = fmaf(LoadS<TI, STAGED>::get(p0 + ch * (int)sizeof(TI)), d_before, acc[ch]);
+                    acc[ch] = fmaf(LoadS<TI, STAGED>::get(p1 + ch * (int)sizeof(TI)), d_after, acc[ch]);
                 }
             };
             for (int q = 0; q < g.ncross; ++q) {  // both left/right edges per packed instruction
@@ -353,9 +485,9 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
 #pragma unroll
             for (int ch = 0; ch < NC; ++ch) {
                 const int o = ch * (int)sizeof(TI);
-                acc[ch] = fmaf(LoadF<TI>::get(p00 + o), W00,
-                               fmaf(LoadF<TI>::get(p01 + o), W01,
-                                    fmaf(LoadF<TI>::get(p10 + o), W10, LoadF<TI>::get(p11 + o) * W11)));
+                acc[ch] = fmaf(LoadS<TI, STAGED>::get(p00 + o), W00,
+                               fmaf(LoadS<TI, STAGED>::get(p01 + o), W01,
+                                    fmaf(LoadS<TI, STAGED>::get(p10 + o), W10, LoadS<TI, STAGED>::get(p11 + o) * W11)));
             }
         }
         // guard band of the quirk decision -> FP64
@@ -378,15 +510,38 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
     }
 }
 
+template <typename TI, typename TO, int NC, int ADDR>
+__global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
+    overlap_kernel_f32(const __grid_constant__ AaiKernelParams kp) {
+    overlap_body<TI, TO, NC, ADDR, false>(kp, nullptr, 0, 0, 0);
+}
+
+// the same kernel with the CTA's source window staged through shared memory by TMA (see "STAGED variants" above)
+template <typename TI, typename TO, int NC>
+__global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
+    overlap_kernel_f32_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ AaiKernelParams kp,
+                           const StageParams sp) {
+    extern __shared__ __align__(128) unsigned char stage_raw[];
+    __shared__ uint64_t bar;
+    int sox, soy;
+    stage_window<(int)sizeof(TI), NC>(&tmap, kp, sp, stage_raw, &bar, kp.ext32, sox, soy);
+    overlap_body<TI, TO, NC, ADDR_IDENT, true>(kp, (const char *)stage_raw, sp.bw * (int)sizeof(TI), sox, soy);
+}
+
 template <typename TI, typename TO, int NC>
 cudaError_t launch3(const AaiKernelParams &kp, cudaStream_t stream) {
     const int rows = kp.row1 - kp.row0;
     if (rows <= 0 || kp.dst_w <= 0) return cudaSuccess;
     dim3 block(TILE_W, TILE_H);
     dim3 grid((kp.dst_w + TILE_W - 1) / TILE_W, (rows + TILE_H - 1) / TILE_H, kp.batch > 1 ? kp.batch : 1);
-    if (kp.scale == 1 && kp.quadrant == 0)
+    if (kp.scale == 1 && kp.quadrant == 0) {
+        StageHost h;
+        if (kp.staged && stage_prepare<TI, NC>(kp, (double)kp.ext32, h)) {
+            overlap_kernel_f32_tma<TI, TO, NC><<<grid, block, h.smem, stream>>>(h.map, kp, h.sp);
+            return cudaGetLastError();
+        }
         overlap_kernel_f32<TI, TO, NC, ADDR_IDENT><<<grid, block, 0, stream>>>(kp);
-    else if (MAXN == 4 && kp.scale >= MAXN - 1)
+    } else if (MAXN == 4 && kp.scale >= MAXN - 1)
         overlap_kernel_f32<TI, TO, NC, (MAXN == 4 ? ADDR_GROUPED : ADDR_GENERAL)><<<grid, block, 0, stream>>>(kp);
     else
         overlap_kernel_f32<TI, TO, NC, ADDR_GENERAL><<<grid, block, 0, stream>>>(kp);
@@ -421,9 +576,9 @@ cudaError_t launch1(const AaiKernelParams &kp, int dst_dtype, cudaStream_t strea
 // (pixel_fast_f64, the reference's own centre expression).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int NF = MAXN - 1;
-template <typename TI, typename TO, int NC, bool IDENT>
-__global__ void __launch_bounds__(TILE_W *TILE_H, 1024 / (TILE_W * TILE_H))
-    fast_kernel_f32u(const __grid_constant__ AaiKernelParams kp) {
+template <typename TI, typename TO, int NC, bool IDENT, bool STAGED>
+__device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char *stage, int spitch, int sox, int soy) {
+    static_assert(!STAGED || IDENT, "staging is implemented for identity addressing");
     const int x = blockIdx.x * TILE_W + threadIdx.x;
     const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
     if (x >= kp.dst_w || y >= kp.row1) return;
@@ -456,7 +611,13 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 1024 / (TILE_W * TILE_H))
             return (int64_t)(kp.scale != 1 ? __umulhi((unsigned)e, kp.div_magic) : (unsigned)e);
         };
         int64_t coff[NF], roff[NF];
-        if (IDENT) {
+        if (STAGED) {  // offsets inside the CTA's shared-memory window
+#pragma unroll
+            for (int k = 0; k < NF; ++k) {
+                coff[k] = ((bx0 + k) * NC - sox) * (int)sizeof(TI);
+                roff[k] = (by0 + k - soy) * spitch;
+            }
+        } else if (IDENT) {
 #pragma unroll
             for (int k = 0; k < NF; ++k) {
                 coff[k] = (int64_t)(bx0 + k) * ESZ;
@@ -476,11 +637,11 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 1024 / (TILE_W * TILE_H))
 #pragma unroll
         for (int r = 0; r < NF; ++r) {
             float v[NF][NC];
-            const char *rowp = (const char *)kp.src + roff[r];
+            const char *rowp = (STAGED ? stage : (const char *)kp.src) + roff[r];
 #pragma unroll
             for (int k = 0; k < NF; ++k)
 #pragma unroll
-                for (int ch = 0; ch < NC; ++ch) v[k][ch] = LoadF<TI>::get(rowp + coff[k] + ch * (int)sizeof(TI));
+                for (int ch = 0; ch < NC; ++ch) v[k][ch] = LoadS<TI, STAGED>::get(rowp + coff[k] + ch * (int)sizeof(TI));
             const float ry = ry0 + (float)r;
             const float ur = -ry * g.sn, vr = ry * g.cs;
 #pragma unroll
@@ -511,16 +672,41 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 1024 / (TILE_W * TILE_H))
     }
 }
 
+template <typename TI, typename TO, int NC, bool IDENT>
+__global__ void __launch_bounds__(TILE_W *TILE_H, 1024 / (TILE_W * TILE_H))
+    fast_kernel_f32u(const __grid_constant__ AaiKernelParams kp) {
+    fast_body<TI, TO, NC, IDENT, false>(kp, nullptr, 0, 0, 0);
+}
+
+// the same kernel with the CTA's source window staged through shared memory by TMA: the default for identity addressing
+// (fast mode is bound by L1 tag wavefronts when it reads through LDG, see "STAGED variants" above)
+template <typename TI, typename TO, int NC>
+__global__ void __launch_bounds__(TILE_W *TILE_H, 1024 / (TILE_W * TILE_H))
+    fast_kernel_f32u_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ AaiKernelParams kp,
+                         const StageParams sp) {
+    extern __shared__ __align__(128) unsigned char stage_raw[];
+    __shared__ uint64_t bar;
+    int sox, soy;
+    stage_window<(int)sizeof(TI), NC>(&tmap, kp, sp, stage_raw, &bar, kp.shapef.hb + 4e-6f, sox, soy);
+    fast_body<TI, TO, NC, true, true>(kp, (const char *)stage_raw, sp.bw * (int)sizeof(TI), sox, soy);
+}
+
 template <typename TI, typename TO, int NC>
 cudaError_t launch_fast3(const AaiKernelParams &kp, cudaStream_t stream) {
     const int rows = kp.row1 - kp.row0;
     if (rows <= 0 || kp.dst_w <= 0) return cudaSuccess;
     dim3 block(TILE_W, TILE_H);
     dim3 grid((kp.dst_w + TILE_W - 1) / TILE_W, (rows + TILE_H - 1) / TILE_H, kp.batch > 1 ? kp.batch : 1);
-    if (kp.scale == 1 && kp.quadrant == 0)
+    if (kp.scale == 1 && kp.quadrant == 0) {
+        StageHost h;
+        if (stage_prepare<TI, NC>(kp, (double)kp.shapef.hb + 1e-5, h)) {
+            fast_kernel_f32u_tma<TI, TO, NC><<<grid, block, h.smem, stream>>>(h.map, kp, h.sp);
+            return cudaGetLastError();
+        }
         fast_kernel_f32u<TI, TO, NC, true><<<grid, block, 0, stream>>>(kp);
-    else
+    } else {
         fast_kernel_f32u<TI, TO, NC, false><<<grid, block, 0, stream>>>(kp);
+    }
     return cudaGetLastError();
 }
 template <typename TI>

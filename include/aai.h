@@ -63,7 +63,12 @@ enum {
 /* Arithmetic of the overlap kernel. */
 enum {
     AAI_ARITH_F64 = 0, /* geometry, areas and accumulation in double (<= 1e-9 relative vs the reference) */
-    AAI_ARITH_F32 = 1  /* geometry + shape decisions in double, area polynomials + accumulation in float */
+    AAI_ARITH_F32 = 1, /* geometry + shape decisions in double, area polynomials + accumulation in float */
+    /* AAI_ARITH_F32 with the overlap kernel's source window staged through shared memory by a 2-D TMA tensor map (the
+     * lay-out BASELINE.json's north star describes).  Same results; measured slower / faster per shape in
+     * profiles/README.md -- the default FP32 kernel reads through L1.  Identity addressing only (scale 1, quadrant 0);
+     * otherwise identical to AAI_ARITH_F32. */
+    AAI_ARITH_F32_STAGED = 2
 };
 
 /*

@@ -282,9 +282,10 @@ extern "C" void aai_test_quadrant_areas(double c, double s, double L, int S, con
         const double X = boundary(ix0, ix1), Y = boundary(jy0, jy1);
         const double irx = std::nearbyint(cx[k]), iry = std::nearbyint(cy[k]);
         const float fx = (float)(cx[k] - irx), fy = (float)(cy[k] - iry);
-        const float tX = X > 1e5 ? gf.q_far : (float)(X - irx) - fx, tY = Y > 1e5 ? gf.q_far : (float)(Y - iry) - fy;
+        const bool hasX = X < 1e5, hasY = Y < 1e5;
+        const float tX = hasX ? (float)(X - irx) - fx : 0.0f, tY = hasY ? (float)(Y - iry) - fy : 0.0f;
         float w[4];
-        aai_quadrant_areas_f32(gf, tX, tY, w[0], w[1], w[2], w[3]);
+        aai_quadrant_areas_f32(gf, tX, tY, hasX, hasY, w[0], w[1], w[2], w[3]);
         double r[4] = {0, 0, 0, 0};
         for (int j = jy0; j <= jy1; ++j)
             for (int i = ix0; i <= ix1; ++i) {

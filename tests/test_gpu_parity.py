@@ -865,3 +865,57 @@ def test_several_devices_reproduce_one_device_bitwise(aai, oracle):
             assert np.array_equal(one.dst, many.dst), (ratio, angle, arith)
         st, want, _ = oracle.run(src, 1.0, ratio, iso, angle, rows=(700, 704))
         assert rel_err(many.dst[700:704], want).max() <= TOL_F32_REL
+
+
+@pytest.mark.parametrize("w,h,ratio,angle,iso,dtype,ch", [
+    (1500, 1100, 0.37, 17.3, (750.0, 550.0), "float32", 1),   # cfg4 shape: MAXN 5
+    (900, 700, 0.37, 30.0, (450.0, 350.0), "uint8", 1),       # cfg2 shape, 8-bit
+    (640, 480, 0.6, 61.0, (320.0, 240.0), "float32", 1),      # theta >= 45: MAXN 4
+    (800, 600, 0.23, 40.0, (400.0, 300.0), "float32", 1),     # L = 4.35: MAXN 8, large window
+    (500, 400, 0.45, 12.0, (10.0, 390.0), "uint8", 3),        # RGB 8-bit, isocentre near a corner
+])
+def test_tma_staged_overlap_kernel_is_bitwise_the_ldg_kernel(aai, oracle, w, h, ratio, angle, iso, dtype, ch):
+    """AAI_ARITH_F32_STAGED (the north star's lay-out: CTA source window staged through shared memory by a 2-D TMA
+    tensor map, cells read with LDS) runs the same arithmetic as AAI_ARITH_F32: identical bits, whole canvas, row bands
+    and a stack of slices; and within tolerance of the oracle."""
+    import torch
+
+    rng = np.random.default_rng(w + h)
+    tail = (ch,) if ch > 1 else ()
+    host = (rng.integers(0, 256, size=(3, h, w) + tail).astype(np.uint8) if dtype == "uint8"
+            else rng.uniform(0, 4096, size=(3, h, w) + tail).astype(np.float32))
+    src = torch.from_numpy(host).cuda()
+    plan = aai.make_plan(w, h, 1.0, ratio, iso, angle)
+    stream = torch.cuda.current_stream().cuda_stream
+    outs = {}
+    for arith in (aai.ARITH_F32, aai.ARITH_F32_STAGED):
+        dst = torch.full((3, plan.dst_h, plan.dst_w) + tail, -1.0, dtype=torch.float32, device="cuda")
+        aai.run_device(plan, aai.tensor_image(src[0]), aai.tensor_image(dst[0]), arith=arith, stream=stream)
+        outs[arith] = dst
+    torch.cuda.synchronize()
+    assert torch.equal(outs[aai.ARITH_F32][0], outs[aai.ARITH_F32_STAGED][0])
+    # row bands (each band holds only its halo rows) and a stack of slices through the staged kernel
+    bands = torch.full_like(outs[aai.ARITH_F32][0], -2.0)
+    from area_average_interpolation_b200.sharding import all_bands
+    for band in all_bands(plan, 3):
+        halo = src[0, band.src_y0:band.src_y1].contiguous()
+        aai.run_device(plan, aai.tensor_image(halo, y0=band.src_y0, height=h), aai.tensor_image(bands), band.row0,
+                       band.row1, arith=aai.ARITH_F32_STAGED, stream=stream)
+    stack = torch.full_like(outs[aai.ARITH_F32], -3.0)
+    aai.run_device_batch(plan, [aai.tensor_image(src[k]) for k in range(3)], [aai.tensor_image(stack[k]) for k in range(3)],
+                         arith=aai.ARITH_F32_STAGED, stream=stream)
+    torch.cuda.synchronize()
+    assert torch.equal(bands, outs[aai.ARITH_F32][0])
+    assert torch.equal(stack[0], outs[aai.ARITH_F32][0])
+    ref2 = torch.empty_like(stack[2])
+    aai.run_device(plan, aai.tensor_image(src[2]), aai.tensor_image(ref2), arith=aai.ARITH_F32, stream=stream)
+    torch.cuda.synchronize()
+    assert torch.equal(stack[2], ref2)
+    got = outs[aai.ARITH_F32_STAGED][0].cpu().numpy().astype(np.float64)
+    for c in range(ch):
+        st, want, _ = oracle.run(host[0], 1.0, ratio, iso, angle, channel=c)
+        g = got[..., c] if ch > 1 else got
+        if dtype == "uint8":
+            assert np.abs(g - want).max() <= TOL_U8_ABS
+        else:
+            assert rel_err(g, want).max() <= TOL_F32_REL

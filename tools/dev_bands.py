@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", type=int, default=4)
 ap.add_argument("--parts", type=int, nargs="+", default=[8])
 ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--json", default="", help="append per-band features + times as JSON lines (cost-model fit)")
 args = ap.parse_args()
 cfg = CONFIGS[args.config]
 dev = torch.device("cuda:0")
@@ -41,6 +42,27 @@ def timed(r0, r1):
     return e0.elapsed_time(e1) / args.steps
 
 
+def features(r0, r1):
+    """Per-band cost-model inputs: rows, canvas pixels, covered pixels, warps (16 x 2 pixel tiles) that hold a covered
+    pixel, span ends (border pixels sit there)."""
+    import ctypes as C
+    lib = aai.lib()
+    cov = warps = ends = 0
+    for y in range(r0 - r0 % 2, r1, 2):
+        lo, hi = None, None
+        for yy in (y, y + 1):
+            if yy < r0 or yy >= r1:
+                continue
+            c = aai.covered_pixels(plan, yy, yy + 1)
+            cov += c
+            if c:
+                ends += 2
+        # span of the row pair from the plan's covered count is not exposed; approximate by the wider of the two rows
+        c2 = max(aai.covered_pixels(plan, max(y, r0), max(y, r0) + 1), aai.covered_pixels(plan, min(y + 1, r1 - 1), min(y + 1, r1 - 1) + 1))
+        warps += (c2 + 15) // 16 + (1 if c2 else 0)
+    return dict(rows=r1 - r0, pixels=(r1 - r0) * plan.dst_w, covered=cov, warps=warps, ends=ends)
+
+
 whole = timed(0, plan.dst_h)
 print(f"whole canvas: {whole:.4f} ms")
 for n in args.parts:
@@ -51,3 +73,10 @@ for n in args.parts:
     print(f"   covered Mpx {[round(c / 1e6, 2) for c in cov]}")
     print(f"   ms {[round(t, 4) for t in ts]}  max {max(ts):.4f}  sum {sum(ts):.4f}  ideal {whole / n:.4f}  "
           f"speed-up {whole / max(ts):.2f}x")
+    if args.json:
+        import json
+        with open(args.json, "a") as f:
+            for k in range(n):
+                d = features(b[k], b[k + 1])
+                d.update(ms=ts[k], parts=n, band=k, config=args.config)
+                f.write(json.dumps(d) + "\n")
