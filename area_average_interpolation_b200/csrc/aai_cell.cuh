@@ -141,7 +141,7 @@ AAI_HD double aai_cell_exact_f64(const AaiShape &g, double rx, double ry, double
 AAI_HD double aai_clamp_chord(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
 
 // Stand-alone form for one (footprint centre, cell) pair: computes the four chords itself.
-AAI_HD double aai_pair_area(const AaiShape &g, double cx, double cy, int i, int j) {
+AAI_HD double aai_pair_area(const AaiShape &g, double cx, double cy, int i, int j, bool quirk = true) {
     const double rx = (double)i - cx, ry = (double)j - cy;
     double xlT, xrT, xlB, xrB, ytL, ybL, ytR, ybR;
     aai_chord_h(g, ry - 0.5, xlT, xrT);
@@ -149,7 +149,7 @@ AAI_HD double aai_pair_area(const AaiShape &g, double cx, double cy, int i, int 
     aai_chord_v(g, rx - 0.5, ytL, ybL);
     aai_chord_v(g, rx + 0.5, ytR, ybR);
     return aai_cell_area(g, rx, ry, aai_overlap1(xlT, xrT, rx), aai_overlap1(xlB, xrB, rx),
-                         aai_overlap1(ytL, ybL, ry), aai_overlap1(ytR, ybR, ry));
+                         aai_overlap1(ytL, ybL, ry), aai_overlap1(ytR, ybR, ry), quirk);
 }
 
 // ------------------------------------------------------------------------------------------------------------

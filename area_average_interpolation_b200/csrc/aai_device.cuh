@@ -198,6 +198,60 @@ __device__ __forceinline__ bool cell_range(const AaiKernelParams &kp, double cx,
     return bx0 < 0 || by0 < 0 || bx1 > kp.mod_w - 1 || by1 > kp.mod_h - 1;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Warp-cooperative FP64 evaluation of the few canvas pixels of a warp that need it (border pixels: the footprint
+// leaves the image and the total area is partial; FP32 guard-band hits).  One lane evaluating its 25-49 cells alone keeps
+// the other 31 lanes of its warp waiting -- for a small image (BASELINE config 2) or the end bands of a multi-GPU
+// partition, whose share of border pixels is high, that was most of the kernel's tail.  Here the 32 lanes take one
+// CELL each of the flagged pixel (exact Green area + the per-cell quirk decision, aai_pair_area; the cell's source
+// value), and the weighted sum and the total area are reduced with warp shuffles.
+// EVERY lane of the warp must call this (no early returns before it); lanes with `need` set receive their pixel's sums.
+// ------------------------------------------------------------------------------------------------------------
+template <typename TI, int NC>
+__device__ __forceinline__ void warp_pixels_f64(const AaiKernelParams &kp, bool need, int x, int y, double &sumA,
+                                                double (&acc)[NC]) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = (threadIdx.y * TILE_W + threadIdx.x) & 31;
+    unsigned todo = __ballot_sync(FULL, need);
+    while (todo) {
+        const int src_lane = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int px = __shfl_sync(FULL, x, src_lane), py = __shfl_sync(FULL, y, src_lane);
+        double cx, cy;
+        pixel_centre(kp, px, py, cx, cy);
+        int i0, i1, j0, j1;
+        cell_range(kp, cx, cy, i0, i1, j0, j1);
+        const int nc = i1 - i0 + 1, ncell = nc > 0 && j1 >= j0 ? nc * (j1 - j0 + 1) : 0;
+        double s = 0.0, a[NC];
+#pragma unroll
+        for (int ch = 0; ch < NC; ++ch) a[ch] = 0.0;
+        for (int c = lane; c < ncell; c += 32) {
+            const int j = j0 + c / nc, i = i0 + c % nc;
+            const double area = aai_pair_area(kp.shape, cx, cy, i, j, kp.quirk != 0);
+            if (area != 0.0) {
+                int sx, sy;
+                mod_to_src(kp, i, j, sx, sy);
+                const char *row = (const char *)kp.src + (int64_t)(sy - src_row0(kp)) * kp.src_pitch;
+                s += area;
+#pragma unroll
+                for (int ch = 0; ch < NC; ++ch) a[ch] += SrcLoad<TI>::get(row, sx * NC + ch) * area;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            s += __shfl_xor_sync(FULL, s, off);
+#pragma unroll
+            for (int ch = 0; ch < NC; ++ch) a[ch] += __shfl_xor_sync(FULL, a[ch], off);
+        }
+        if (lane == src_lane) {
+            sumA = s;
+#pragma unroll
+            for (int ch = 0; ch < NC; ++ch) acc[ch] = a[ch];
+        }
+    }
+}
+
 }  // namespace aai_dev
 
 #endif  // AAI_DEVICE_CUH_

@@ -66,6 +66,8 @@ int aai_launch_expand(const AaiKernelParams &kp, int elem_bytes, void *stream);
 int aai_probe_fp32(int blocks, int iters, float *scratch, double *flop, void *stream);
 // aai_kernels_sep.cu: TMA-staged separable kernel; returns cudaErrorNotSupported when its fast path does not apply
 int aai_launch_separable_tma(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream);
+// aai_kernels_sep.cu: FP32 direct-tap kernel for axis-aligned cases outside the TMA kernel's preconditions
+int aai_launch_separable_direct_f32(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
 // aai_kernels_f32.cu, one translation unit per maximum cell count per axis
 int aai_launch_overlap_f32_n4(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_overlap_f32_n5(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);

@@ -289,8 +289,12 @@ int aai_probe_fp32(int blocks, int iters, float *scratch, double *flop, void *st
 }
 int aai_launch_separable(const AaiKernelParams &kp, int arith, int src_dtype, int dst_dtype, void *stream) {
     // TMA-staged two-pass kernel when its preconditions hold, else direct taps
-    const int e = aai_launch_separable_tma(kp, arith, src_dtype, dst_dtype, stream);
+    int e = aai_launch_separable_tma(kp, arith, src_dtype, dst_dtype, stream);
     if (e != (int)cudaErrorNotSupported) return e;
+    if (arith == AAI_ARITH_F32) {  // quadrants 1-3, scale > 1, RGB: FP32 direct taps
+        e = aai_launch_separable_direct_f32(kp, src_dtype, dst_dtype, stream);
+        if (e != (int)cudaErrorNotSupported) return e;
+    }
     return (int)launch_any(K_SEPARABLE, kp, src_dtype, dst_dtype, (cudaStream_t)stream);
 }
 int aai_launch_expand(const AaiKernelParams &kp, int elem_bytes, void *stream) {

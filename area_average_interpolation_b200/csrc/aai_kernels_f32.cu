@@ -99,35 +99,37 @@ __device__ __forceinline__ uint32_t st_smem_u32(const void *p) { return (uint32_
 // because the window misses the image.
 template <int EB, int NC>  // EB = bytes per element, NC = interleaved channels
 __device__ __forceinline__ void stage_window(const CUtensorMap *tmap, const AaiKernelParams &kp, const StageParams &sp,
-                                             unsigned char *smem, uint64_t *bar, float ext, int &sox, int &soy) {
-    const int x0 = blockIdx.x * TILE_W, y0 = kp.row0 + blockIdx.y * TILE_H;
-    double lox = 1e300, loy = 1e300;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {  // the centre map is affine: the extremes sit at the tile's corners
-        const double xx = (double)(x0 + (c & 1) * (TILE_W - 1)), yy = (double)(y0 + (c >> 1) * (TILE_H - 1));
-        lox = fmin(lox, fma(xx, kp.aff_xx, fma(yy, kp.aff_xy, kp.aff_x0)));
-        loy = fmin(loy, fma(xx, kp.aff_yx, fma(yy, kp.aff_yy, kp.aff_y0)));
-    }
-    constexpr int EAL = 16 / EB;  // elements per 16 bytes: the TMA start coordinate must be a multiple of it
-    int ex = (__double2int_rd(lox - (double)ext) - 1) * NC;
-    ex = (ex >= 0 ? ex / EAL : -((-ex + EAL - 1) / EAL)) * EAL;
-    sox = ex;
-    soy = __double2int_rd(loy - (double)ext) - 1;
+                                             unsigned char *smem, uint64_t *bar, int *origin, float ext, int &sox,
+                                             int &soy) {
     const int tid = threadIdx.y * TILE_W + threadIdx.x;
-    if (tid == 0) {
+    if (tid == 0) {  // one thread: window origin (FP64, the centre map is affine: extremes at the tile's corners), TMA
+        const int x0 = blockIdx.x * TILE_W, y0 = kp.row0 + blockIdx.y * TILE_H;
+        double lox = 1e300, loy = 1e300;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const double xx = (double)(x0 + (c & 1) * (TILE_W - 1)), yy = (double)(y0 + (c >> 1) * (TILE_H - 1));
+            lox = fmin(lox, fma(xx, kp.aff_xx, fma(yy, kp.aff_xy, kp.aff_x0)));
+            loy = fmin(loy, fma(xx, kp.aff_yx, fma(yy, kp.aff_yy, kp.aff_y0)));
+        }
+        constexpr int EAL = 16 / EB;  // elements per 16 bytes: the TMA start coordinate must be a multiple of it
+        int ex = (__double2int_rd(lox - (double)ext) - 1) * NC;
+        ex = (ex >= 0 ? ex / EAL : -((-ex + EAL - 1) / EAL)) * EAL;
+        const int ey = __double2int_rd(loy - (double)ext) - 1;
+        origin[0] = ex;
+        origin[1] = ey;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(bar)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
         const uint32_t bytes = (uint32_t)(sp.bw * sp.bh * EB);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(st_smem_u32(bar)), "r"(bytes) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
                 "r"(st_smem_u32(smem)),
-            "l"(tmap), "r"(st_smem_u32(bar)), "r"(sox), "r"(soy - src_row0(kp))
+            "l"(tmap), "r"(st_smem_u32(bar)), "r"(ex), "r"(ey - src_row0(kp))
             : "memory");
     }
+    __syncthreads();  // barrier initialised, origin visible
+    sox = origin[0];
+    soy = origin[1];
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -223,9 +225,10 @@ template <typename TI, typename TO, int NC, int ADDR, bool STAGED>
 __device__ __forceinline__ void overlap_body(const AaiKernelParams &kp, const char *stage, int spitch, int sox, int soy) {
     constexpr bool IDENT = ADDR == ADDR_IDENT, GROUPED = ADDR == ADDR_GROUPED;
     static_assert(!STAGED || IDENT, "staging is implemented for identity addressing");
+    // (no early return: every lane of a warp reaches the cooperative FP64 section at the end)
     const int x = blockIdx.x * TILE_W + threadIdx.x;
     const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
-    if (x >= kp.dst_w || y >= kp.row1) return;
+    const bool valid = x < kp.dst_w && y < kp.row1;
     // Footprint centre from the affine form of Source.cpp:212-219 (two FP64 FMAs per coordinate; within ~1e-12 of
     // the reference's own expression, pixel_centre(), which the FP64 redo path below evaluates), split into the nearest
     // lattice point and an FP32 fraction.
@@ -241,10 +244,10 @@ __device__ __forceinline__ void overlap_body(const AaiKernelParams &kp, const ch
     const bool border = bx0 < 0 || by0 < 0 || bx1 > kp.mod_w - 1 || by1 > kp.mod_h - 1;
     const int ncols = ix1 - ix0 + 1, nrows = jy1 - jy0 + 1;
     char *drow = (char *)kp.dst + (int64_t)(y - dst_row0(kp)) * kp.dst_pitch;
-    if (ncols <= 0 || nrows <= 0) {  // footprint bounding box misses the image: the reference writes 0 (577)
+    const bool work = valid && ncols > 0 && nrows > 0;
+    if (valid && !work) {  // footprint bounding box misses the image: the reference writes 0 (577)
 #pragma unroll
         for (int ch = 0; ch < NC; ++ch) store_f<TO>(drow, x * NC + ch, 0.0f);
-        return;
     }
     float sumA = 0.0f, acc[NC];
 #pragma unroll
@@ -252,8 +255,8 @@ __device__ __forceinline__ void overlap_body(const AaiKernelParams &kp, const ch
     float worst = 1.0f;
     // Border pixels (footprint partly outside the image) are normalised by a partial, possibly tiny, total area:
     // they need relative accuracy, so they take the FP64 path (~0.1% of a large canvas).
-    bool redo = border || ncols > MAXN || nrows > MAXN || ncols < MINC;  // (the MAXN test cannot fire for the MAXN the host picked)
-    if (!redo) {
+    bool redo = work && (border || ncols > MAXN || nrows > MAXN || ncols < MINC);  // (the MAXN test cannot fire for the MAXN the host picked)
+    if (work && !redo) {
         const AaiShapeF &g = kp.shapef;
         const int dj0 = jy0 - iry;
         const float rx0 = (float)(ix0 - irx) - fx;
@@ -493,17 +496,14 @@ __device__ __forceinline__ void overlap_body(const AaiKernelParams &kp, const ch
         // guard band of the quirk decision -> FP64
         redo = worst < g.tau || sumA < 0.25f;
     }
+    // rare path, warp-cooperative: the flagged pixels of this warp one after the other, one CELL per lane
+    double s64 = 0.0, a64[NC];
+    if (__any_sync(0xffffffffu, redo)) warp_pixels_f64<TI, NC>(kp, redo, x, y, s64, a64);
     if (redo) {
-        // rare path: geometry recomputed here so that it does not occupy registers across the FP32 loop
-        double s64, a64[NC], cx2, cy2;
-        int i0, i1, j0, j1;
-        pixel_centre(kp, x, y, cx2, cy2);
-        cell_range(kp, cx2, cy2, i0, i1, j0, j1);
-        pixel_f64<TI, NC>(kp, cx2, cy2, i0, i1, j0, j1, s64, a64);
         const bool ok = DBL_EPSILON < fabs(s64);
 #pragma unroll
         for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, ok ? a64[ch] / s64 : 0.0);
-    } else {
+    } else if (work) {
         const float inv = 1.0f / sumA;
 #pragma unroll
         for (int ch = 0; ch < NC; ++ch) store_f<TO>(drow, x * NC + ch, acc[ch] * inv);
@@ -523,8 +523,9 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
                            const StageParams sp) {
     extern __shared__ __align__(128) unsigned char stage_raw[];
     __shared__ uint64_t bar;
+    __shared__ int origin[2];
     int sox, soy;
-    stage_window<(int)sizeof(TI), NC>(&tmap, kp, sp, stage_raw, &bar, kp.ext32, sox, soy);
+    stage_window<(int)sizeof(TI), NC>(&tmap, kp, sp, stage_raw, &bar, origin, kp.ext32, sox, soy);
     overlap_body<TI, TO, NC, ADDR_IDENT, true>(kp, (const char *)stage_raw, sp.bw * (int)sizeof(TI), sox, soy);
 }
 
@@ -686,8 +687,9 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 1024 / (TILE_W * TILE_H))
                          const StageParams sp) {
     extern __shared__ __align__(128) unsigned char stage_raw[];
     __shared__ uint64_t bar;
+    __shared__ int origin[2];
     int sox, soy;
-    stage_window<(int)sizeof(TI), NC>(&tmap, kp, sp, stage_raw, &bar, kp.shapef.hb + 4e-6f, sox, soy);
+    stage_window<(int)sizeof(TI), NC>(&tmap, kp, sp, stage_raw, &bar, origin, kp.shapef.hb + 4e-6f, sox, soy);
     fast_body<TI, TO, NC, true, true>(kp, (const char *)stage_raw, sp.bw * (int)sizeof(TI), sox, soy);
 }
 

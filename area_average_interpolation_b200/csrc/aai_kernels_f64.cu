@@ -8,8 +8,9 @@
 // inside the image is L^2, and the reference's shape-2/4 quirk is one pair of corrected cells per minor-axis grid line
 // that a left/right edge crosses (aai_edge_quirk_f64).  Decisions are made directly on FP64 margins computed from the
 // reference's own expression of the footprint centre (pixel_centre): no guard band, no redo.  Border pixels (footprint
-// partly outside the image: partial total area) and footprints wider than MAXN take the generic per-cell routine
-// pixel_f64 (aai_device.cuh), which is also the whole of the rolled kernel overlap_kernel_f64 in aai_kernels.cu.
+// partly outside the image: partial total area) and footprints wider than MAXN take the per-cell routine, evaluated
+// warp-cooperatively (warp_pixels_f64 in aai_device.cuh: one cell per lane, shuffle reduction); the rolled kernel
+// overlap_kernel_f64 in aai_kernels.cu runs the per-cell routine for every pixel (pixel_f64).
 #include "aai_device.cuh"
 
 #ifndef AAI_MAXN
@@ -25,24 +26,25 @@ constexpr int MAXN = AAI_MAXN;
 template <typename TI, typename TO, int NC, bool IDENT>
 __global__ void __launch_bounds__(TILE_W *TILE_H, 512 / (TILE_W *TILE_H))
     overlap_kernel_f64u(const __grid_constant__ AaiKernelParams kp) {
+    // (no early return: every lane of a warp reaches the cooperative section below)
     const int x = blockIdx.x * TILE_W + threadIdx.x;
     const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
-    if (x >= kp.dst_w || y >= kp.row1) return;
+    const bool valid = x < kp.dst_w && y < kp.row1;
     double cx, cy;
     pixel_centre(kp, x, y, cx, cy);
     int ix0, ix1, jy0, jy1;
     const bool border = cell_range(kp, cx, cy, ix0, ix1, jy0, jy1);
     const int ncols = ix1 - ix0 + 1, nrows = jy1 - jy0 + 1;
     char *drow = (char *)kp.dst + (int64_t)(y - dst_row0(kp)) * kp.dst_pitch;
-    if (ncols <= 0 || nrows <= 0) {  // footprint bounding box misses the image: the reference writes 0 (577)
+    const bool work = valid && ncols > 0 && nrows > 0;
+    if (valid && !work) {  // footprint bounding box misses the image: the reference writes 0 (577)
 #pragma unroll
         for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, 0.0);
-        return;
     }
-    double sumA, acc[NC];
-    if (border || ncols > MAXN || nrows > MAXN) {
-        pixel_f64<TI, NC>(kp, cx, cy, ix0, ix1, jy0, jy1, sumA, acc);
-    } else {
+    double sumA = 0.0, acc[NC];
+    // border pixels (partial total area) and footprints wider than MAXN: per-cell routine, one cell per lane of the warp
+    const bool coop = work && (border || ncols > MAXN || nrows > MAXN);
+    if (work && !coop) {
         const AaiShape &g = kp.shape;
 #pragma unroll
         for (int ch = 0; ch < NC; ++ch) acc[ch] = 0.0;
@@ -146,9 +148,12 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 512 / (TILE_W *TILE_H))
             }
         }
     }
-    const bool ok = DBL_EPSILON < fabs(sumA);  // Source.cpp:577
+    if (__any_sync(0xffffffffu, coop)) warp_pixels_f64<TI, NC>(kp, coop, x, y, sumA, acc);
+    if (work) {
+        const bool ok = DBL_EPSILON < fabs(sumA);  // Source.cpp:577
 #pragma unroll
-    for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, ok ? acc[ch] / sumA : 0.0);
+        for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, ok ? acc[ch] / sumA : 0.0);
+    }
 }
 
 template <typename TI, typename TO, int NC>

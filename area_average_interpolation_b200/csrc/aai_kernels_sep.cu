@@ -506,6 +506,97 @@ cudaError_t launch_sep_src(const AaiKernelParams &kp, int src_dtype, int dst_dty
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Axis-aligned cases OUTSIDE the TMA kernel's preconditions -- a quadrant pre-rotation (90 / 180 / 270 degrees,
+// Source.cpp:163-168), an integer expansion (scale > 1), interleaved RGB -- in FP32 arithmetic: direct taps, fully
+// unrolled.  Same weights as the TMA kernel (axis_taps<float>: the footprint interval against the unit cells of the
+// expanded frame, in-image cells only), the cells found through the separable byte offset col_off(i) + row_off(j) of
+// the expanded-frame index map (as in the FP32 overlap kernel), MAXT x MAXT loads per canvas pixel through L1.
+// (Before round 2 these cases ran on the FP64 direct-tap kernel with a division per tap.)
+// ------------------------------------------------------------------------------------------------------------
+template <typename TI, typename TO, int NC, int MAXT>
+__global__ void __launch_bounds__(TILE_W *TILE_H)
+    separable_direct_f32(const __grid_constant__ AaiKernelParams kp) {
+    const int x = blockIdx.x * TILE_W + threadIdx.x;
+    const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
+    if (x >= kp.dst_w || y >= kp.row1) return;
+    double cx, cy;
+    pixel_centre(kp, x, y, cx, cy);
+    const double h = kp.shape.half;
+    float wx[MAXT], wy[MAXT], sumx, sumy;
+    int fx0, fy0;
+    axis_taps<float, MAXT>(cx, h, kp.mod_w, fx0, wx, sumx);
+    axis_taps<float, MAXT>(cy, h, kp.mod_h, fy0, wy, sumy);
+    constexpr int ESZ = (int)sizeof(TI) * NC;
+    const bool swapped = kp.e_axi == 0;
+    auto div_s = [&](int e) -> int64_t {
+        return (int64_t)(kp.scale != 1 ? __umulhi((unsigned)e, kp.div_magic) : (unsigned)e);
+    };
+    int64_t coff[MAXT], roff[MAXT];
+#pragma unroll
+    for (int k = 0; k < MAXT; ++k) {  // out-of-image taps carry weight 0: clamp their address into the image
+        const int i = min(max(fx0 + k, 0), kp.mod_w - 1), j = min(max(fy0 + k, 0), kp.mod_h - 1);
+        coff[k] = swapped ? (div_s(kp.e_ayi * i + kp.e_ay0) - src_row0(kp)) * kp.src_pitch
+                          : div_s(kp.e_axi * i + kp.e_ax0) * ESZ;
+        roff[k] = swapped ? div_s(kp.e_axj * j + kp.e_ax0) * ESZ
+                          : (div_s(kp.e_ayj * j + kp.e_ay0) - src_row0(kp)) * kp.src_pitch;
+    }
+    float acc[NC];
+#pragma unroll
+    for (int ch = 0; ch < NC; ++ch) acc[ch] = 0.0f;
+#pragma unroll
+    for (int r = 0; r < MAXT; ++r) {
+        const char *rowp = (const char *)kp.src + roff[r];
+        float hs[NC];
+#pragma unroll
+        for (int ch = 0; ch < NC; ++ch) hs[ch] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < MAXT; ++k)
+#pragma unroll
+            for (int ch = 0; ch < NC; ++ch)
+                hs[ch] += wx[k] * (float)__ldg(reinterpret_cast<const TI *>(rowp + coff[k]) + ch);
+#pragma unroll
+        for (int ch = 0; ch < NC; ++ch) acc[ch] += wy[r] * hs[ch];
+    }
+    char *drow = (char *)kp.dst + (int64_t)(y - dst_row0(kp)) * kp.dst_pitch;
+    const float total = sumx * sumy;
+#pragma unroll
+    for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, (double)sep_normalise<float>(acc[ch], total));
+}
+
+template <typename TI, typename TO, int NC>
+cudaError_t launch_direct_taps(const AaiKernelParams &kp, cudaStream_t stream) {
+    const double L = 2.0 * kp.shape.half;
+    const int taps = (int)ceil(L - 1e-12) + 1;
+    const int rows = kp.row1 - kp.row0;
+    dim3 block(TILE_W, TILE_H);
+    dim3 grid((kp.dst_w + TILE_W - 1) / TILE_W, (rows + TILE_H - 1) / TILE_H, kp.batch > 1 ? kp.batch : 1);
+    if (taps <= 3)
+        separable_direct_f32<TI, TO, NC, 3><<<grid, block, 0, stream>>>(kp);
+    else if (taps <= 4)
+        separable_direct_f32<TI, TO, NC, 4><<<grid, block, 0, stream>>>(kp);
+    else if (taps <= 6)
+        separable_direct_f32<TI, TO, NC, 6><<<grid, block, 0, stream>>>(kp);
+    else
+        return cudaErrorNotSupported;
+    return cudaGetLastError();
+}
+template <typename TI, typename TO>
+cudaError_t launch_direct_ch(const AaiKernelParams &kp, cudaStream_t stream) {
+    if (kp.channels == 1) return launch_direct_taps<TI, TO, 1>(kp, stream);
+    if (kp.channels == 3) return launch_direct_taps<TI, TO, 3>(kp, stream);
+    return cudaErrorNotSupported;
+}
+template <typename TI>
+cudaError_t launch_direct_dst(const AaiKernelParams &kp, int dst_dtype, cudaStream_t stream) {
+    switch (dst_dtype) {
+        case AAI_F32: return launch_direct_ch<TI, float>(kp, stream);
+        case AAI_U8: return launch_direct_ch<TI, uint8_t>(kp, stream);
+        default: return cudaErrorNotSupported;  // double destinations keep FP64 arithmetic
+    }
+}
+
 }  // namespace
 
 // Returns cudaErrorNotSupported (as int) when the TMA fast path does not apply.
@@ -516,4 +607,18 @@ int aai_launch_separable_tma(const AaiKernelParams &kp, int arith, int src_dtype
     cudaStream_t st = (cudaStream_t)stream;
     if (arith == AAI_ARITH_F32 && src_dtype != AAI_F64) return (int)launch_sep_src<float>(kp, src_dtype, dst_dtype, st);
     return (int)launch_sep_src<double>(kp, src_dtype, dst_dtype, st);
+}
+
+// FP32 direct-tap kernel for the axis-aligned cases the TMA kernel does not take (quadrants 1-3, scale > 1, RGB);
+// cudaErrorNotSupported -> the caller falls back to the FP64 direct-tap kernel.
+int aai_launch_separable_direct_f32(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream) {
+    const uint64_t max_e = (uint64_t)(kp.mod_w > kp.mod_h ? kp.mod_w : kp.mod_h);
+    if (max_e * (uint64_t)kp.scale >= 0x100000000ULL) return (int)cudaErrorNotSupported;  // multiply-high division range
+    if (kp.row1 <= kp.row0 || kp.dst_w <= 0) return (int)cudaSuccess;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (src_dtype) {
+        case AAI_F32: return (int)launch_direct_dst<float>(kp, dst_dtype, st);
+        case AAI_U8: return (int)launch_direct_dst<uint8_t>(kp, dst_dtype, st);
+        default: return (int)cudaErrorNotSupported;
+    }
 }

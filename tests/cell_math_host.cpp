@@ -305,3 +305,73 @@ extern "C" void aai_test_quadrant_areas(double c, double s, double L, int S, con
         }
     }
 }
+
+// Whole-image evaluation with the arithmetic of the FP32 kernel's UPSCALING path (ADDR_GROUPED: quadrant weights +
+// per-edge quirk events booked per source pixel), TEST ONLY.  `mod` is the expanded + quadrant-rotated source
+// (modH x modW); the source-pixel groups along an axis are given by the expanded coordinate e = a * i + e0 (a = +-1)
+// and the scale S.  flag: 1 = the kernel would redo the pixel in FP64 (guard band / border), out is then not filled.
+extern "C" void aai_test_image_grouped_f32(double c, double s, double L, double offIx, double offIy, double isoX,
+                                           double isoY, double offX, double offY, int modW, int modH, int dstW, int dstH,
+                                           int S, int ac, int ec0, int ar, int er0, const double *mod, double *out,
+                                           unsigned char *flag) {
+    const AaiShapeF g = make_shape_f(c, s, L);
+    const double h = L / 2;
+    const float ext32 = (float)(h * (c + s) + 0.5 + 2e-6);
+    auto first_group = [&](int e, int step) { const int rem = ((e % S) + S) % S; return step > 0 ? S - rem : rem + 1; };
+    for (int y = 0; y < dstH; ++y)
+        for (int x = 0; x < dstW; ++x) {
+            const size_t idx = (size_t)y * dstW + x;
+            const double u = ((x + offIx) * L - isoX) + offX, v = ((y + offIy) * L - isoY) + offY;
+            const double cx = (u * c + v * s) + isoX, cy = (-u * s + v * c) + isoY;
+            const int irx = (int)std::nearbyint(cx), iry = (int)std::nearbyint(cy);
+            const float fx = (float)(cx - irx), fy = (float)(cy - iry);
+            const int bx0 = irx + (int)std::ceil(fx - ext32), bx1 = irx + (int)std::floor(fx + ext32);
+            const int by0 = iry + (int)std::ceil(fy - ext32), by1 = iry + (int)std::floor(fy + ext32);
+            const int ix0 = std::max(0, bx0), ix1 = std::min(modW - 1, bx1), jy0 = std::max(0, by0), jy1 = std::min(modH - 1, by1);
+            const int ncols = ix1 - ix0 + 1, nrows = jy1 - jy0 + 1;
+            out[idx] = 0.0;
+            flag[idx] = 0;
+            if (ncols <= 0 || nrows <= 0) continue;
+            if (bx0 < 0 || by0 < 0 || bx1 > modW - 1 || by1 > modH - 1 || ncols > 4 || nrows > 4) {
+                flag[idx] = 1;
+                continue;
+            }
+            const int dj0 = jy0 - iry;
+            const float rx0 = (float)(ix0 - irx) - fx, t0 = ((float)dj0 - fy) - 0.5f, e0 = rx0 - 0.5f;
+            const int nA = first_group(ac * ix0 + ec0, ac), nT = first_group(ar * jy0 + er0, ar);
+            float W00, W01, W10, W11;
+            aai_quadrant_areas_f32(g, e0 + (float)nA, t0 + (float)nT, nA < ncols, nT < nrows, W00, W01, W10, W11);
+            float sumA = g.area_total, worst = 1.0f;
+            const float g0m = g.steep ? e0 : t0, g0M = g.steep ? t0 : e0;
+            for (int q = 0; q < g.ncross; ++q) {
+                int mi[2], Mi[2];
+                float db[2], da[2];
+                aai_edge_quirk_pair_f32(g, g0m, g0M, q, mi, Mi, db, da, worst);
+                for (int e = 0; e < 2; ++e) {
+                    const int mlim = (g.steep ? ncols : nrows) - 2, Mlim = (g.steep ? nrows : ncols) - 1;
+                    const int m = std::max(0, std::min(mi[e], mlim)), M = std::max(0, std::min(Mi[e], Mlim));
+                    const int k = g.steep ? m : M, r = g.steep ? M : m;
+                    const int k1 = k + (g.steep ? 1 : 0), r1 = r + (g.steep ? 0 : 1);
+                    const float both = db[e] + da[e];
+                    if (g.steep) {
+                        const float dA = (k < nA ? db[e] : 0.0f) + (k1 < nA ? da[e] : 0.0f), dB = both - dA;
+                        const bool top = r < nT;
+                        W00 += top ? dA : 0.0f; W01 += top ? dB : 0.0f; W10 += top ? 0.0f : dA; W11 += top ? 0.0f : dB;
+                    } else {
+                        const float dT = (r < nT ? db[e] : 0.0f) + (r1 < nT ? da[e] : 0.0f), dBt = both - dT;
+                        const bool left = k < nA;
+                        W00 += left ? dT : 0.0f; W10 += left ? dBt : 0.0f; W01 += left ? 0.0f : dT; W11 += left ? 0.0f : dBt;
+                    }
+                    sumA += both;
+                }
+            }
+            const float v00 = (float)mod[(size_t)jy0 * modW + ix0], v01 = (float)mod[(size_t)jy0 * modW + ix1];
+            const float v10 = (float)mod[(size_t)jy1 * modW + ix0], v11 = (float)mod[(size_t)jy1 * modW + ix1];
+            const float acc = fmaf(v00, W00, fmaf(v01, W01, fmaf(v10, W10, v11 * W11)));
+            if (worst < g.tau || sumA < 0.25f) {
+                flag[idx] = 1;
+                continue;
+            }
+            out[idx] = (double)(acc * (1.0f / sumA));
+        }
+}

@@ -4,7 +4,7 @@ size-independent properties plus oracle-checked sample rows."""
 import numpy as np
 import pytest
 
-from common import TOL_F64_REL, TOL_F32_REL, TOL_U8_ABS, golden_source, load_golden, rel_err
+from common import TOL_F64_REL, TOL_F32_REL, TOL_U8_ABS, f32_err, golden_source, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -160,8 +160,7 @@ def test_fast_mode_fp32_kernel_matches_oracle(aai, oracle, w, h, ratio, angle, i
     r = _run(aai, src, 1.0, ratio, iso, angle, mode=2, arith=aai.ARITH_F32, out_dtype=np.float32)
     st, want, wiso = oracle.run(src, 1.0, ratio, iso, angle, mode=2)
     assert st == 0 and want.shape == r.dst.shape and wiso == r.dst_isocenter
-    err = np.abs(r.dst.astype(np.float64) - want) / np.maximum(np.abs(want), 1e-30)
-    err[want == 0] = np.abs(r.dst[want == 0])
+    err = f32_err(r.dst, want, 4096.0)
     bad = err > TOL_F32_REL
     if bad.any():
         case = dict(src_res=1.0, dst_res=ratio, iso=iso, angle=angle, mode=2)
@@ -183,8 +182,7 @@ def test_f32_kernel_matches_oracle_on_float_data(aai, oracle, w, h, ratio, angle
     r = _run(aai, src, 1.0, ratio, iso, angle, arith=aai.ARITH_F32, out_dtype=np.float32)
     st, want, wiso = oracle.run(src, 1.0, ratio, iso, angle)
     assert st == 0 and want.shape == r.dst.shape and wiso == r.dst_isocenter
-    err = np.abs(r.dst.astype(np.float64) - want) / np.maximum(np.abs(want), 1e-30)
-    err[want == 0] = np.abs(r.dst[want == 0])
+    err = f32_err(r.dst, want, 4096.0)
     assert err.max() <= TOL_F32_REL, (float(err.max()), int((err > TOL_F32_REL).sum()))
 
 
@@ -199,7 +197,7 @@ def test_f32_kernel_on_8bit_data_and_golden_vectors(aai, oracle):
         r = _run(aai, src, case["src_res"], case["dst_res"], case["iso"], case["angle"], arith=aai.ARITH_F32,
                  out_dtype=np.float32)
         st, want, _ = oracle.run(src, case["src_res"], case["dst_res"], case["iso"], case["angle"])
-        tol = TOL_U8_ABS if src.dtype == np.uint8 else TOL_F32_REL * np.maximum(np.abs(want), 1e-30)
+        tol = TOL_U8_ABS if src.dtype == np.uint8 else TOL_F32_REL * np.maximum(np.abs(want), float(src.max()) / 256.0)
         assert (np.abs(r.dst - want) <= tol).all(), case["name"]
     rng = np.random.default_rng(12)
     rgb = rng.integers(0, 256, size=(300, 260, 3), dtype=np.uint8)
@@ -221,8 +219,7 @@ def test_f32_kernel_symmetric_ties_and_near_axis_angles(aai, oracle):
                                 (0.6, 88.5, (128.0, 128.0)), (0.6, 5.0, (128.0, 128.0))]:
         r = _run(aai, src, 1.0, ratio, iso, angle, arith=aai.ARITH_F32, out_dtype=np.float32)
         st, want, _ = oracle.run(src, 1.0, ratio, iso, angle)
-        err = np.abs(r.dst - want) / np.maximum(np.abs(want), 1e-30)
-        err[want == 0] = np.abs(r.dst[want == 0])
+        err = f32_err(r.dst, want, 255.0)
         assert err.max() <= TOL_F32_REL, (ratio, angle, float(err.max()))
 
 
@@ -336,7 +333,7 @@ def test_batch_of_slices_is_one_launch_and_matches_per_image_runs(aai, oracle):
     torch.cuda.synchronize()
     assert torch.equal(dst, ref)
     st, want, _ = oracle.run(src[3].cpu().numpy(), 1.0, 0.5, (100.0, 84.0), 0.0)
-    assert (np.abs(dst[3].cpu().numpy() - want) <= TOL_F32_REL * np.maximum(np.abs(want), 1e-30)).all()
+    assert f32_err(dst[3].cpu().numpy(), want, 4096.0).max() <= TOL_F32_REL
     # not equally strided (reversed order): falls back to one launch per image, same results
     order = [4, 2, 0]
     out2 = torch.empty(3, plan.dst_h, plan.dst_w, dtype=torch.float32, device="cuda")
@@ -390,9 +387,12 @@ def test_batch_of_rotated_slices_is_one_launch(aai, oracle, ratio, angle, iso, d
         for c in range(ch):
             st, want, _ = oracle.run(plane[..., c] if ch > 1 else plane, 1.0, ratio, iso, angle, mode=mode)
             assert st == 0
-            tol = TOL_F32_REL if arith == 1 else TOL_F64_REL
             gc = got[..., c] if ch > 1 else got
-            assert rel_err(gc, want).max() <= tol
+            if dtype == "uint8" and arith == 1:  # north star: 0.5/255 absolute on 8-bit data for the FP32 kernel
+                assert np.abs(gc - want).max() <= TOL_U8_ABS
+            else:
+                err = f32_err(gc, want, 4096.0) if arith == 1 else rel_err(gc, want)
+                assert err.max() <= (TOL_F32_REL if arith == 1 else TOL_F64_REL)
 
 
 def test_device_image_helpers_roundtrip(aai):
@@ -465,8 +465,7 @@ def test_random_configurations_both_kernels(aai, oracle, w, h, ratio, angle, iso
     r32 = _run(aai, src, 1.0, ratio, iso, angle, arith=aai.ARITH_F32, out_dtype=np.float32)
     assert r64.dst.shape == want.shape and r64.dst_isocenter == wiso and r32.dst.shape == want.shape
     bad64 = rel_err(r64.dst, want) > TOL_F64_REL
-    e32 = np.abs(r32.dst.astype(np.float64) - want) / np.maximum(np.abs(want), 1e-30)
-    e32[want == 0] = np.abs(r32.dst[want == 0])
+    e32 = f32_err(r32.dst, want, 4096.0)
     bad32 = e32 > TOL_F32_REL
     if bad64.any() or bad32.any():
         case = dict(src_res=1.0, dst_res=ratio, iso=iso, angle=angle, mode=1)
@@ -500,8 +499,7 @@ def test_separable_tma_path_matches_oracle(aai, oracle, w, h, ratio, iso):
     src32 = src.astype(np.float32)
     st, want32, _ = oracle.run(src32, 1.0, ratio, iso, 0.0)
     r32 = _run(aai, src32, 1.0, ratio, iso, 0.0, arith=aai.ARITH_F32, out_dtype=np.float32)
-    err = np.abs(r32.dst.astype(np.float64) - want32) / np.maximum(np.abs(want32), 1e-30)
-    err[want32 == 0] = np.abs(r32.dst[want32 == 0])
+    err = f32_err(r32.dst, want32, 255.0)
     assert err.max() <= TOL_F32_REL, float(err.max())
     src8 = src.astype(np.uint8)
     st, want8, _ = oracle.run(src8, 1.0, ratio, iso, 0.0)
@@ -564,8 +562,7 @@ def test_exact_mode_matches_its_clipping_checker(aai, oracle, w, h, ratio, angle
     op32 = aai.AreaAverageInterpolation(arith=aai.ARITH_F32, out_dtype=np.float32)
     r32 = op32.exactAreaAverageInterpolation(src.astype(np.float32), 1.0, ratio, iso, angle)
     st, want32, _ = oracle.run(src.astype(np.float32), 1.0, ratio, iso, angle, mode=3)
-    err = np.abs(r32.dst.astype(np.float64) - want32) / np.maximum(np.abs(want32), 1e-30)
-    err[want32 == 0] = np.abs(r32.dst[want32 == 0])
+    err = f32_err(r32.dst, want32, 4096.0)
     assert err.max() <= TOL_F32_REL, (float(err.max()), int((err > TOL_F32_REL).sum()))
 
 
@@ -616,12 +613,10 @@ def test_full_size_cfg4_sample_rows_and_properties(aai, oracle):
         st, want, _ = oracle.run(src, 1.0, 0.37, (8192.0, 8192.0), 17.3, rows=(row, row + 1))
         err = rel_err(out[row:row + 1], want)
         assert err.max() <= TOL_F64_REL, (row, float(err.max()))
-        e32 = np.abs(out32[row:row + 1] - want) / np.maximum(np.abs(want), 1e-30)
-        e32[want == 0] = np.abs(out32[row:row + 1][want == 0])
+        e32 = f32_err(out32[row:row + 1], want, 4096.0)
         assert e32.max() <= TOL_F32_REL, (row, float(e32.max()))
     # FP32 and FP64 kernels agree over the WHOLE canvas (the FP64 one is oracle-checked on the sample rows above)
-    whole = np.abs(out32 - out) / np.maximum(np.abs(out), 1e-30)
-    whole[out == 0] = np.abs(out32[out == 0])
+    whole = f32_err(out32, out, 4096.0)
     assert whole.max() <= TOL_F32_REL, float(whole.max())
     frac = (out != 0).mean()
     assert 0.62 < frac < 0.65  # covered fraction 0.638
@@ -675,8 +670,8 @@ def test_full_size_cfg5_slice_axis_aligned(aai, oracle):
 # ---- BASELINE shapes at FULL size on the benchmarked paths (VERDICT r1 "missing" 1) ----------------------------------
 
 def _f32_err(got, want):
-    """Relative error of an FP32-kernel result (absolute where the reference value is exactly 0)."""
-    return rel_err(np.asarray(got, dtype=np.float64), want)
+    """Error of an FP32-kernel result on the 12-bit synthetic float data (tests/common.py: f32_err)."""
+    return f32_err(got, want, 4096.0)
 
 
 def test_full_size_cfg1_u8_whole_image(aai, oracle):
@@ -846,7 +841,8 @@ def test_canvas_taller_than_the_grid_limit(aai, oracle):
             if mode == 2:  # centre-in ties at exactly symmetric geometry are decided by rounding noise (see fast-mode tests)
                 assert (rel_err(got, want) <= 1e-5).mean() > 0.6
             else:
-                assert rel_err(got, want).max() <= (TOL_F32_REL if arith == aai.ARITH_F32 else TOL_F64_REL), (angle, r0)
+                err = f32_err(got, want, 4096.0) if arith == aai.ARITH_F32 else rel_err(got, want)
+                assert err.max() <= (TOL_F32_REL if arith == aai.ARITH_F32 else TOL_F64_REL), (angle, r0)
 
 
 def test_several_devices_reproduce_one_device_bitwise(aai, oracle):
@@ -864,7 +860,7 @@ def test_several_devices_reproduce_one_device_bitwise(aai, oracle):
             many = _run(aai, src, 1.0, ratio, iso, angle, arith=arith, out_dtype=od, devices=list(range(n)))
             assert np.array_equal(one.dst, many.dst), (ratio, angle, arith)
         st, want, _ = oracle.run(src, 1.0, ratio, iso, angle, rows=(700, 704))
-        assert rel_err(many.dst[700:704], want).max() <= TOL_F32_REL
+        assert f32_err(many.dst[700:704], want, 4096.0).max() <= TOL_F32_REL
 
 
 @pytest.mark.parametrize("w,h,ratio,angle,iso,dtype,ch", [
@@ -918,4 +914,49 @@ def test_tma_staged_overlap_kernel_is_bitwise_the_ldg_kernel(aai, oracle, w, h, 
         if dtype == "uint8":
             assert np.abs(g - want).max() <= TOL_U8_ABS
         else:
-            assert rel_err(g, want).max() <= TOL_F32_REL
+            assert f32_err(g, want, 4096.0).max() <= TOL_F32_REL
+
+
+@pytest.mark.parametrize("w,h,ratio,angle,iso,dtype,ch", [
+    (640, 480, 0.5, 90.0, (320.0, 240.0), "float32", 1),     # a plain quarter turn
+    (640, 480, 0.5, 180.0, (320.5, 239.5), "uint8", 3),      # RGB, half turn, half-integer isocentre
+    (333, 517, 0.37, 270.0, (100.0, 400.0), "uint8", 1),     # L = 2.70: 4 taps
+    (300, 200, 1.0, 0.0, (150.0, 100.0), "uint8", 3),        # scale 2 (expanded frame), RGB, no rotation
+    (300, 200, 2.0, 90.0, (150.0, 100.0), "float32", 1),     # scale 3 + quarter turn
+    (500, 400, 0.23, 180.0, (250.0, 200.0), "float32", 3),   # L = 4.35: 6 taps, three float channels
+])
+def test_axis_aligned_fp32_direct_tap_kernel_matches_oracle(aai, oracle, w, h, ratio, angle, iso, dtype, ch):
+    """Axis-aligned cases outside the TMA kernel's preconditions (quadrant pre-rotation Source.cpp:163-168, integer
+    expansion, RGB) in FP32 arithmetic: unrolled direct-tap kernel; float and 8-bit canvases; bands bitwise."""
+    import torch
+
+    rng = np.random.default_rng(w * 3 + h)
+    tail = (ch,) if ch > 1 else ()
+    host = (rng.integers(0, 256, size=(h, w) + tail).astype(np.uint8) if dtype == "uint8"
+            else rng.uniform(0, 4096, size=(h, w) + tail).astype(np.float32))
+    plan = aai.make_plan(w, h, 1.0, ratio, iso, angle)
+    assert plan.axis_aligned == 1
+    src = torch.from_numpy(host).cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+    dst = torch.full((plan.dst_h, plan.dst_w) + tail, -1.0, dtype=torch.float32, device="cuda")
+    aai.run_device(plan, aai.tensor_image(src), aai.tensor_image(dst), arith=aai.ARITH_F32, stream=stream)
+    parts = torch.full_like(dst, -2.0)
+    cuts = [0, min(5, plan.dst_h), min(61, plan.dst_h), plan.dst_h]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        aai.run_device(plan, aai.tensor_image(src), aai.tensor_image(parts), a, b, arith=aai.ARITH_F32, stream=stream)
+    torch.cuda.synchronize()
+    assert torch.equal(dst, parts)
+    got = dst.cpu().numpy().astype(np.float64)
+    for c in range(ch):
+        st, want, _ = oracle.run(host, 1.0, ratio, iso, angle, channel=c)
+        assert st == 0
+        g = got[..., c] if ch > 1 else got
+        if dtype == "uint8":
+            assert np.abs(g - want).max() <= TOL_U8_ABS, (c, float(np.abs(g - want).max()))
+        else:
+            assert f32_err(g, want, 4096.0).max() <= TOL_F32_REL, (c, float(f32_err(g, want, 4096.0).max()))
+    if dtype == "uint8":
+        d8 = torch.zeros((plan.dst_h, plan.dst_w) + tail, dtype=torch.uint8, device="cuda")
+        aai.run_device(plan, aai.tensor_image(src), aai.tensor_image(d8), arith=aai.ARITH_F32, stream=stream)
+        torch.cuda.synchronize()
+        assert np.abs(d8.cpu().numpy().astype(np.float64) - got).max() <= 0.5 + 1e-3

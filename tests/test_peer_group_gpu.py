@@ -9,7 +9,7 @@ import time
 import numpy as np
 import pytest
 
-from common import TOL_F32_REL, rel_err
+from common import TOL_F32_REL, f32_err
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -147,4 +147,4 @@ def test_host_batch_pipeline_matches_per_image_runs(aai, built):
             # (the single-image host path may take the other axis-aligned kernel for its pitched buffer: rounding only)
             assert np.allclose(dst[k].numpy(), one, rtol=2e-6, atol=1e-5), k
             st, want, _ = port.run(src[k].numpy(), 1.0, ratio, iso, angle)
-            assert rel_err(dst[k].numpy(), want).max() <= TOL_F32_REL
+            assert f32_err(dst[k].numpy(), want, 4096.0).max() <= TOL_F32_REL

@@ -22,7 +22,10 @@ for r in csv.reader(out.splitlines()):
             continue
         key = (cur, int(r[0]))
         agg[key] += n
-        samp[key] += int(d.get("# Samples", "0") or 0)
+        try:
+            samp[key] += int(d.get("# Samples", "0") or 0)
+        except ValueError:
+            pass
         src[key] = r[1]
 tot, stot = sum(agg.values()) or 1, sum(samp.values()) or 1
 print(f"total warp instructions {tot}, samples {stot}")
