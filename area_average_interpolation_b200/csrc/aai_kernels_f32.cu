@@ -78,12 +78,13 @@ __device__ __forceinline__ void store_f<uint8_t>(void *row, int idx, float v) {
 
 
 // ------------------------------------------------------------------------------------------------------------
-// STAGED variants (the north star's lay-out): the source window of a CTA's 16 x 8 canvas pixels is brought into shared
-// memory by ONE 2-D TMA tile load (cp.async.bulk.tensor.2d through a CUtensorMap, completion on an mbarrier) and the
-// cells are read with LDS instead of LDG.  Footprints of a rotated canvas row step through the source diagonally, so a
-// warp's 32 loads of "cell k" hit ~28 different 32-byte sectors -- 28 L1 tag wavefronts per LDG -- while the same 32
-// addresses in shared memory cost ~3 bank-conflict wavefronts.  Fast mode (16 loads and ~9 other instructions per cell)
-// is limited by exactly that; the overlap kernel (135 instructions per row of 5 cells) is not.
+// STAGED variants (the north star's lay-out, selected with AAI_ARITH_F32_STAGED): the source window of a CTA's 16 x 8
+// canvas pixels is brought into shared memory by ONE 2-D TMA tile load (cp.async.bulk.tensor.2d through a CUtensorMap,
+// completion on an mbarrier) and the cells are read with LDS instead of LDG.  Footprints of a rotated canvas row step
+// through the source diagonally, so a warp's 32 loads of "cell k" hit ~28 different 32-byte sectors -- 28 L1 tag
+// wavefronts per LDG -- while the same 32 addresses in shared memory cost ~2.6 bank-conflict wavefronts.  Measured
+// (profiles/README.md, round 2): that relief does not pay for the per-CTA load latency -- overlap kernel 1.475 ms staged
+// against 1.386 ms through L1 on BASELINE config 4, fast mode 0.658 against 0.616 ms -- so both default to LDG.
 // Identity addressing only (scale 1, quadrant 0); the window origin is rounded down to a 16-byte boundary (TMA
 // requirement); out-of-image parts of the box are zero-filled by the hardware and never read (pixels whose footprint
 // box leaves the image take the FP64 path, which reads global memory).
@@ -679,8 +680,9 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 1024 / (TILE_W * TILE_H))
     fast_body<TI, TO, NC, IDENT, false>(kp, nullptr, 0, 0, 0);
 }
 
-// the same kernel with the CTA's source window staged through shared memory by TMA: the default for identity addressing
-// (fast mode is bound by L1 tag wavefronts when it reads through LDG, see "STAGED variants" above)
+// the same kernel with the CTA's source window staged through shared memory by TMA (AAI_ARITH_F32_STAGED).  Measured on
+// BASELINE config 4: 0.658 ms against 0.616 ms for the LDG kernel -- the L1 tag stage is relieved (77 % -> 42 %), but every
+// CTA now waits for its own TMA load before its ~250 instructions per thread (stalls: long_scoreboard 36 %, barrier 17 %)
 template <typename TI, typename TO, int NC>
 __global__ void __launch_bounds__(TILE_W *TILE_H, 1024 / (TILE_W * TILE_H))
     fast_kernel_f32u_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ AaiKernelParams kp,
@@ -701,7 +703,7 @@ cudaError_t launch_fast3(const AaiKernelParams &kp, cudaStream_t stream) {
     dim3 grid((kp.dst_w + TILE_W - 1) / TILE_W, (rows + TILE_H - 1) / TILE_H, kp.batch > 1 ? kp.batch : 1);
     if (kp.scale == 1 && kp.quadrant == 0) {
         StageHost h;
-        if (stage_prepare<TI, NC>(kp, (double)kp.shapef.hb + 1e-5, h)) {
+        if (kp.staged && stage_prepare<TI, NC>(kp, (double)kp.shapef.hb + 1e-5, h)) {  // A/B variant (AAI_ARITH_F32_STAGED)
             fast_kernel_f32u_tma<TI, TO, NC><<<grid, block, h.smem, stream>>>(h.map, kp, h.sp);
             return cudaGetLastError();
         }

@@ -890,6 +890,14 @@ def test_tma_staged_overlap_kernel_is_bitwise_the_ldg_kernel(aai, oracle, w, h, 
         outs[arith] = dst
     torch.cuda.synchronize()
     assert torch.equal(outs[aai.ARITH_F32][0], outs[aai.ARITH_F32_STAGED][0])
+    # fast mode has the same pair of kernels
+    fast = {}
+    for arith in (aai.ARITH_F32, aai.ARITH_F32_STAGED):
+        fast[arith] = torch.full((plan.dst_h, plan.dst_w) + tail, -1.0, dtype=torch.float32, device="cuda")
+        aai.run_device(plan, aai.tensor_image(src[1]), aai.tensor_image(fast[arith]), mode=aai.MODE_FAST, arith=arith,
+                       stream=stream)
+    torch.cuda.synchronize()
+    assert torch.equal(fast[aai.ARITH_F32], fast[aai.ARITH_F32_STAGED])
     # row bands (each band holds only its halo rows) and a stack of slices through the staged kernel
     bands = torch.full_like(outs[aai.ARITH_F32][0], -2.0)
     from area_average_interpolation_b200.sharding import all_bands
