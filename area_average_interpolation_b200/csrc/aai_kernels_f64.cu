@@ -22,6 +22,9 @@ using namespace aai_dev;
 namespace {
 
 constexpr int MAXN = AAI_MAXN;
+#ifndef AAI_F64_COOP
+#define AAI_F64_COOP 1  // border pixels warp-cooperative (0: each lane alone, the round-1 form; A/B in profiles/README.md)
+#endif
 
 template <typename TI, typename TO, int NC, bool IDENT>
 __global__ void __launch_bounds__(TILE_W *TILE_H, 512 / (TILE_W *TILE_H))
@@ -29,7 +32,12 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 512 / (TILE_W *TILE_H))
     // (no early return: every lane of a warp reaches the cooperative section below)
     const int x = blockIdx.x * TILE_W + threadIdx.x;
     const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
+#if AAI_F64_COOP
     const bool valid = x < kp.dst_w && y < kp.row1;
+#else
+    if (x >= kp.dst_w || y >= kp.row1) return;
+    constexpr bool valid = true;
+#endif
     double cx, cy;
     pixel_centre(kp, x, y, cx, cy);
     int ix0, ix1, jy0, jy1;
@@ -40,6 +48,9 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 512 / (TILE_W *TILE_H))
     if (valid && !work) {  // footprint bounding box misses the image: the reference writes 0 (577)
 #pragma unroll
         for (int ch = 0; ch < NC; ++ch) store_dst<TO>(drow, x * NC + ch, 0.0);
+#if !AAI_F64_COOP
+        return;
+#endif
     }
     double sumA = 0.0, acc[NC];
     // border pixels (partial total area) and footprints wider than MAXN: per-cell routine, one cell per lane of the warp
@@ -148,7 +159,11 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 512 / (TILE_W *TILE_H))
             }
         }
     }
+#if AAI_F64_COOP
     if (__any_sync(0xffffffffu, coop)) warp_pixels_f64<TI, NC>(kp, coop, x, y, sumA, acc);
+#else
+    if (coop) pixel_f64<TI, NC>(kp, cx, cy, ix0, ix1, jy0, jy1, sumA, acc);
+#endif
     if (work) {
         const bool ok = DBL_EPSILON < fabs(sumA);  // Source.cpp:577
 #pragma unroll

@@ -18,7 +18,7 @@ cpu_baseline = the reference's own CPU implementation (compiled upstream Source.
             bounded replica of the workload, timed on this box (rank 0, N = 1)
 verified  = after the timed regions: the canvas the end-to-end path produced is (a) bitwise equal to the band computed
             from a source generated directly in HBM (independent of the upload / NVLink exchange) and (b) within
-            tolerance of the CPU oracle on the first and last row of every rank's band
+            tolerance of the CPU oracle on the first, middle and last row of every rank's band
 configs   = the other BASELINE shapes (cfg 1, 2, 3, 5), the FP64 kernel and fast mode on the headline shape, measured
             the same way in the same run outside the headline's timed regions (all ranks take part under torchrun)
 
@@ -549,8 +549,8 @@ class Bench:
 
     def _verify(self, cfg, cfg_id, plan, mode, arith, band, dev_dst, host_dst, step, seed, first_image):
         """(a) the end-to-end canvas equals, bit for bit, the canvas computed from the HBM-generated source (the upload /
-        NVLink exchange delivered exactly the right bytes to the right rows); (b) first and last row of this rank's band
-        (first / last slice of a batch) against the CPU oracle."""
+        NVLink exchange delivered exactly the right bytes to the right rows); (b) first, middle and last row of this rank's
+        band (first / last slice of a batch) against the CPU oracle."""
         torch, aai = self.torch, self.aai
         from area_average_interpolation_b200.synthetic import synthetic_image_torch
 
@@ -571,7 +571,7 @@ class Bench:
             got = got.numpy()
             u8 = np_dt == np.uint8
             if band is not None:
-                rows = sorted({band.row0, band.row1 - 1}) if band.rows > 0 else []
+                rows = sorted({band.row0, (band.row0 + band.row1) // 2, band.row1 - 1}) if band.rows > 0 else []
                 for r in rows:
                     _, _, sy0, sy1 = aai.band_source_window(plan, r, r + 1)
                     if sy1 <= sy0:
