@@ -138,6 +138,10 @@ def lib() -> C.CDLL:
         L.aai_peer_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(Image), C.POINTER(Image), C.c_void_p, C.c_int]
         L.aai_peer_device_source.restype = C.c_int
         L.aai_peer_device_source.argtypes = [C.c_void_p, C.POINTER(Image)]
+        L.aai_peer_upload_chunks.restype = C.c_int
+        L.aai_peer_upload_chunks.argtypes = [C.c_int]
+        L.aai_peer_last_timing.restype = C.c_int
+        L.aai_peer_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.aai_peer_destroy.restype = C.c_int
         L.aai_peer_destroy.argtypes = [C.c_void_p]
         L.aai_launch_count.restype = C.c_int64
@@ -345,6 +349,11 @@ def run_host_batch(plan: Plan, src_imgs: Sequence[Image], dst_imgs: Sequence[Ima
 PEER_BLOB_BYTES = 2048
 
 
+def peer_upload_chunks(n: int = 0) -> int:
+    """``aai_peer_upload_chunks``: upload chunks per owner rank of a peer group (1..8, default 4); 0 only queries."""
+    return int(lib().aai_peer_upload_chunks(int(n)))
+
+
 class PeerGroup:
     """``aai_peer_*`` (include/aai.h): ONE large image over one process per GPU, end to end from host buffers -- every
     source row crosses PCIe once, halos move over NVLink, no NCCL and no barrier per step.
@@ -387,6 +396,12 @@ class PeerGroup:
             stream: int = 0, synchronize: bool = True) -> None:
         _check(lib().aai_peer_run(self._h, int(mode), int(arith), C.byref(host_src), C.byref(host_dst),
                                   C.c_void_p(stream), int(bool(synchronize))))
+
+    def last_timing(self) -> dict:
+        """Completion times [ms from the start of the last step] of this rank's upload, pulls, kernels, downloads."""
+        ms = (C.c_float * 4)()
+        _check(lib().aai_peer_last_timing(self._h, ms))
+        return {"upload_ms": ms[0], "pull_ms": ms[1], "kernel_ms": ms[2], "download_ms": ms[3]}
 
     def close(self) -> None:
         if self._h:

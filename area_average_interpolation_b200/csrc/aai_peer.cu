@@ -26,7 +26,7 @@
 
 namespace {
 
-constexpr int kMaxChunks = 24;        // upload chunks per owner (an IPC event each)
+constexpr int kMaxChunks = 8;         // upload chunks per owner (an IPC event each)
 constexpr uint32_t kMagic = 0x41414950;  // "AAIP"
 constexpr double kHostWaitSeconds = 60.0;
 
@@ -72,6 +72,8 @@ struct aai_peer {
     aai_image band{};                    // device canvas band (allocated by the first step)
     cudaStream_t own = nullptr, up = nullptr, pl = nullptr, dn = nullptr;
     cudaEvent_t fork = nullptr, join_up = nullptr, join_pl = nullptr, join_dn = nullptr;
+    cudaEvent_t t_fork = nullptr, t_up = nullptr, t_pl = nullptr, t_k = nullptr, t_dn = nullptr;  // phase timing of the last step
+    bool timed = false;
     cudaEvent_t landed[kMaxChunks] = {};  // own upload chunks (interprocess events, also waited on locally)
     cudaEvent_t pulled = nullptr;         // own "pulls of this step are done" (interprocess)
     std::vector<cudaEvent_t> op_ev, k_ev;  // local: after each pull op / each kernel chunk
@@ -99,11 +101,15 @@ void owned_rows(int64_t h, int world, int p, int64_t &y0, int64_t &y1) {
     y1 = h * (p + 1) / world;
 }
 
-// upload chunks of an owner: ~16 MB each, at most kMaxChunks; every rank computes the same split
+// upload chunks of an owner: four (so that the pulls of the first quarters overlap the upload of the later ones), fewer
+// when that would make them smaller than 8 MB -- every chunk costs an interprocess event wait per reader, and at 8 ranks
+// the uploads of all owners run concurrently anyway; every rank computes the same split
+std::atomic<int> g_upload_chunks{4};
 int chunk_count(int64_t rows, int64_t row_bytes) {
     if (rows <= 0) return 0;
-    int64_t n = (rows * row_bytes + (16 << 20) - 1) / (16 << 20);
+    int64_t n = rows * row_bytes / (8 << 20);
     if (n < 1) n = 1;
+    if (n > g_upload_chunks.load()) n = g_upload_chunks.load();
     if (n > kMaxChunks) n = kMaxChunks;
     if (n > rows) n = rows;
     return (int)n;
@@ -138,6 +144,11 @@ int copy_rows_2d(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitc
 }  // namespace
 
 extern "C" {
+
+int aai_peer_upload_chunks(int n) {
+    if (n >= 1 && n <= kMaxChunks) g_upload_chunks.store(n);
+    return g_upload_chunks.load();
+}
 
 int aai_peer_create(const aai_plan *plan, int32_t dtype, int32_t channels, int rank, int world_size, int device,
                     aai_peer **out) {
@@ -181,6 +192,7 @@ int aai_peer_create(const aai_plan *plan, int32_t dtype, int32_t channels, int r
     ok(cudaStreamCreateWithFlags(&g->dn, cudaStreamNonBlocking));
     for (cudaEvent_t *ev : {&g->fork, &g->join_up, &g->join_pl, &g->join_dn})
         ok(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    for (cudaEvent_t *ev : {&g->t_fork, &g->t_up, &g->t_pl, &g->t_k, &g->t_dn}) ok(cudaEventCreate(ev));
     for (int c = 0; c < kMaxChunks; ++c)
         ok(cudaEventCreateWithFlags(&g->landed[c], cudaEventDisableTiming | cudaEventInterprocess));
     ok(cudaEventCreateWithFlags(&g->pulled, cudaEventDisableTiming | cudaEventInterprocess));
@@ -332,6 +344,7 @@ int aai_peer_run(aai_peer *g, int mode, int arith, const aai_image *hsrc, const 
     // fork: the internal streams start after everything already queued on the caller's stream (in particular after the
     // previous step of this group, which joined back into it: its kernels no longer read the device image)
     PEER_CUDA(cudaEventRecord(g->fork, st));
+    PEER_CUDA(cudaEventRecord(g->t_fork, st));
     for (cudaStream_t q : {g->up, g->pl, g->dn}) PEER_CUDA(cudaStreamWaitEvent(q, g->fork, 0));
 
     // 1. my rows may be overwritten once every reader has finished pulling them in the previous step
@@ -356,6 +369,7 @@ int aai_peer_run(aai_peer *g, int mode, int arith, const aai_image *hsrc, const 
         if (rc != AAI_OK) return rc;
         PEER_CUDA(cudaEventRecord(g->landed[c], g->up));
     }
+    PEER_CUDA(cudaEventRecord(g->t_up, g->up));
     g->shm->up_issued.store(s, std::memory_order_release);
 
     // 3. pull the rows of my halo that others own, chunk-major (round robin over the owners, so that the pulls track
@@ -403,11 +417,12 @@ int aai_peer_run(aai_peer *g, int mode, int arith, const aai_image *hsrc, const 
             ++n_pull;
         }
     PEER_CUDA(cudaEventRecord(g->pulled, g->pl));
+    PEER_CUDA(cudaEventRecord(g->t_pl, g->pl));
     g->shm->pull_issued.store(s, std::memory_order_release);
 
     // 4. kernels + downloads, chunk by chunk, each kernel after the last op that completes a row range it reads
     const int64_t band_rows = g->row1 - g->row0;
-    int chunks = band_rows >= 64 ? (int)std::min<int64_t>(16, band_rows / 16) : 1;
+    int chunks = band_rows >= 64 ? (int)std::min<int64_t>(8, band_rows / 16) : 1;
     if (band_rows <= 0) chunks = 0;
     while ((int)g->k_ev.size() < chunks) {
         cudaEvent_t e;
@@ -434,6 +449,9 @@ int aai_peer_run(aai_peer *g, int mode, int arith, const aai_image *hsrc, const 
                                      g->band.pitch_bytes, (size_t)dst_row_bytes, r1 - r0, cudaMemcpyDeviceToHost, g->dn);
         if (rc2 != AAI_OK) return rc2;
     }
+    PEER_CUDA(cudaEventRecord(g->t_k, st));
+    PEER_CUDA(cudaEventRecord(g->t_dn, g->dn));
+    g->timed = true;
     // join: the caller's stream continues after the uploads, the pulls and the downloads
     PEER_CUDA(cudaEventRecord(g->join_up, g->up));
     PEER_CUDA(cudaEventRecord(g->join_pl, g->pl));
@@ -442,6 +460,17 @@ int aai_peer_run(aai_peer *g, int mode, int arith, const aai_image *hsrc, const 
     PEER_CUDA(cudaStreamWaitEvent(st, g->join_pl, 0));
     PEER_CUDA(cudaStreamWaitEvent(st, g->join_dn, 0));
     if (synchronize || !stream) PEER_CUDA(cudaStreamSynchronize(st));
+    return AAI_OK;
+}
+
+int aai_peer_last_timing(aai_peer *g, float ms[4]) {
+    if (!g || !ms || !g->timed) return AAI_ERR_ARGUMENT;
+    PEER_CUDA(cudaSetDevice(g->device));
+    cudaEvent_t ev[4] = {g->t_up, g->t_pl, g->t_k, g->t_dn};
+    for (int k = 0; k < 4; ++k) {
+        PEER_CUDA(cudaEventSynchronize(ev[k]));
+        PEER_CUDA(cudaEventElapsedTime(&ms[k], g->t_fork, ev[k]));
+    }
     return AAI_OK;
 }
 
@@ -463,7 +492,7 @@ int aai_peer_destroy(aai_peer *g) {
     if (g->pulled) cudaEventDestroy(g->pulled);
     for (cudaEvent_t e : g->op_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : g->k_ev) cudaEventDestroy(e);
-    for (cudaEvent_t e : {g->fork, g->join_up, g->join_pl, g->join_dn})
+    for (cudaEvent_t e : {g->fork, g->join_up, g->join_pl, g->join_dn, g->t_fork, g->t_up, g->t_pl, g->t_k, g->t_dn})
         if (e) cudaEventDestroy(e);
     for (cudaStream_t q : {g->own, g->up, g->pl, g->dn})
         if (q) cudaStreamDestroy(q);

@@ -413,6 +413,8 @@ class Bench:
                 hdi = aai.tensor_image(host_dst, y0=band.row0, height=plan.dst_h)
                 d2h = band.rows * plan.dst_w * CH * osz
                 if world > 1 and not args.no_peer:
+                    if args.peer_chunks:
+                        aai.peer_upload_chunks(args.peer_chunks)
                     try:
                         peer = aai.PeerGroup(plan, aai._NP_TO_AAI[np_dt], CH, rank, world, local, self.gather)
                     except Exception as exc:  # IPC unavailable: every rank uploads its own halo from the host
@@ -477,6 +479,9 @@ class Bench:
             e2e = {"value": total_pixels / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
                    "h2d_bytes_per_step": self.sum_over_ranks(float(h2d)),
                    "d2h_bytes_per_step": self.sum_over_ranks(float(d2h)), "ms_per_step": e2e_ms}
+            if peer is not None:  # device-side completion times of the last step's phases, per rank (from its start)
+                ph = self.gather(peer.last_timing())
+                e2e["phases_ms_per_rank"] = {k: [round(p[k], 3) for p in ph] for k in ph[0]}
         clocks = sampler.stop() if sampler else {}
 
         # ---- verification (outside the timed regions) ----------------------------------------------------------------
@@ -687,6 +692,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="headline workload only (skip the `configs` record)")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--peer-chunks", type=int, default=0, help="N>1: upload chunks per owner rank of the peer group (1..8)")
     ap.add_argument("--no-peer", action="store_true",
                     help="N>1: every rank uploads its whole halo from the host instead of NVLink peer copies")
     args = ap.parse_args()

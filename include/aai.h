@@ -229,6 +229,10 @@ int aai_run_host_batch(const aai_plan *plan, int mode, int arith, const aai_imag
  * identical to one GPU (all ranks share the plan). */
 typedef struct aai_peer aai_peer;
 #define AAI_PEER_BLOB_BYTES 2048
+/* Tuning knob (process-wide, read by aai_peer_create; every rank must use the same value): into how many chunks an
+ * owner cuts its upload, 1..8, default 4.  More chunks let the NVLink pulls start earlier, but every chunk costs each
+ * reader one interprocess event wait.  Returns the value in force (n outside 1..8 only queries). */
+int aai_peer_upload_chunks(int n);
 int aai_peer_create(const aai_plan *plan, int32_t dtype, int32_t channels, int rank, int world_size, int device,
                     aai_peer **out);
 int aai_peer_export(aai_peer *peer, unsigned char blob[AAI_PEER_BLOB_BYTES]);
@@ -245,6 +249,9 @@ int aai_peer_run(aai_peer *peer, int mode, int arith, const aai_image *host_src,
 /* The rank's full-size device source image (rows of the band's halo are valid after a step) -- for device-resident
  * follow-up work (aai_run_device). */
 int aai_peer_device_source(const aai_peer *peer, aai_image *out);
+/* Device-side phase times [ms] of this rank's LAST step, measured from the start of the step: own upload complete, last
+ * halo pull complete, last kernel complete, last download complete (waits for the step to finish). */
+int aai_peer_last_timing(aai_peer *peer, float ms[4]);
 /* Frees the group's device memory and IPC mappings.  Call it once every rank has completed its last step (any barrier
  * of the launcher): peers read this rank's device image. */
 int aai_peer_destroy(aai_peer *peer);

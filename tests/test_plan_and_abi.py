@@ -82,7 +82,7 @@ def test_axis_aligned_flag(aai):
         assert aai.make_plan(32, 32, 1.0, 0.5, (16, 16), ang).axis_aligned == flag, ang
 
 
-def test_partition_covers_canvas_and_balances_covered_pixels(aai):
+def test_partition_covers_canvas_and_balances_kernel_cost(aai):
     p = aai.make_plan(16384, 16384, 1.0, 0.37, (8192, 8192), 17.3)
     assert (p.dst_w, p.dst_h) == (7591, 7591)
     total = aai.covered_pixels(p)
@@ -92,7 +92,11 @@ def test_partition_covers_canvas_and_balances_covered_pixels(aai):
         assert b[0] == 0 and b[-1] == p.dst_h and all(b[i] < b[i + 1] for i in range(n))
         loads = [aai.covered_pixels(p, b[i], b[i + 1]) for i in range(n)]
         assert sum(loads) == total
-        assert max(loads) <= 1.05 * total / n, (n, loads)
+        # the split equalises the measured cost model (covered pixels + 0.16 per empty canvas pixel, aai_plan.cpp), so
+        # the bands at the canvas corners (many rows, short spans) hold fewer covered pixels than the middle ones
+        cost = [loads[i] + 0.16 * ((b[i + 1] - b[i]) * p.dst_w - loads[i]) for i in range(n)]
+        assert max(cost) <= 1.01 * sum(cost) / n, (n, cost)
+        assert max(loads) <= 1.10 * total / n, (n, loads)
 
 
 def test_band_source_window_contains_every_pixel_the_oracle_reads(aai):
