@@ -356,7 +356,7 @@ def peer_upload_chunks(n: int = 0) -> int:
 
 class PeerGroup:
     """``aai_peer_*`` (include/aai.h): ONE large image over one process per GPU, end to end from host buffers -- every
-    source row crosses PCIe once, halos move over NVLink, no NCCL and no barrier per step.
+    source row crosses PCIe once, halos move over NVLink as the upload chunks land, no NCCL and no barrier per step.
 
     ``all_gather(obj) -> list`` is the caller's out-of-band channel (e.g. ``torch.distributed.all_gather_object``), used
     once to exchange the connection blobs."""

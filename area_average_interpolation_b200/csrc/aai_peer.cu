@@ -2,13 +2,14 @@
 //
 // Every source row crosses PCIe once (its owner rank uploads it, in chunks, into the owner's full-size device image);
 // the rows of a band's halo that the rank does not own are pulled out of the owners' device images over NVLink (CUDA IPC
-// memory mappings) as the chunks land.  "Chunk c of owner p has landed" is an INTERPROCESS CUDA EVENT: the reader's copy
-// stream waits on it on the device.  cudaStreamWaitEvent captures the event's most recent record at the time of the
-// call, so the host side orders the enqueueing -- a reader waits on an owner's events only after the owner has
-// re-recorded them for this step, an owner overwrites its rows only after every reader has recorded "my pulls of the
-// previous step are done" -- through two monotonic counters per rank in a POSIX shared-memory page.  No NCCL, no
-// barrier: the bands are independent (the reference's loop nest Source.cpp:413-415 has no cross-pixel
-// dependency).
+// memory mappings) as the chunks land.  The ranks synchronise through two monotonic counters per rank in a POSIX
+// shared-memory page -- "upload chunks landed" and "steps whose pulls are complete" -- driven by the host: the calling
+// thread polls its own upload events (cudaEventQuery) and publishes them, polls the owners' counters and enqueues each
+// pull the moment its chunk has landed.  (A first version expressed the same dependencies with interprocess CUDA
+// events waited on by the copy streams; measured on 8 B200s every such wait cost milliseconds -- 13.3 ms per step
+// against 9.0 ms for round 1's barrier scheme -- so the device-side waits were dropped; profiles/README.md.)
+// No NCCL, no barrier: the bands are independent (the reference's loop nest Source.cpp:413-415 has no
+// cross-pixel dependency).
 #include <cuda_runtime.h>
 #include <fcntl.h>
 #include <sched.h>
@@ -31,8 +32,8 @@ constexpr uint32_t kMagic = 0x41414950;  // "AAIP"
 constexpr double kHostWaitSeconds = 60.0;
 
 struct PeerShm {  // one page of POSIX shared memory per rank
-    std::atomic<uint64_t> up_issued;    // last step whose upload events this rank has recorded
-    std::atomic<uint64_t> pull_issued;  // last step whose "pulls done" event this rank has recorded
+    std::atomic<uint64_t> landed;  // upload chunks of this rank that have arrived in its device image, over all steps
+    std::atomic<uint64_t> pulled;  // last step whose halo pulls this rank has completed (its peers' rows may be reused)
 };
 
 #pragma pack(push, 1)
@@ -41,8 +42,6 @@ struct Blob {
     int32_t rank, world, n_chunks;
     int64_t pitch;
     cudaIpcMemHandle_t mem;
-    cudaIpcEventHandle_t landed[kMaxChunks];
-    cudaIpcEventHandle_t pulled;
     char shm_name[64];
 };
 #pragma pack(pop)
@@ -53,8 +52,6 @@ int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 struct Remote {  // what this rank knows about rank p
     void *full = nullptr;                 // p's device image, mapped here (nullptr for p == rank)
-    cudaEvent_t landed[kMaxChunks] = {};  // opened IPC events
-    cudaEvent_t pulled = nullptr;
     PeerShm *shm = nullptr;
     int n_chunks = 0;
     int64_t y0 = 0, y1 = 0;               // rows p owns
@@ -74,8 +71,8 @@ struct aai_peer {
     cudaEvent_t fork = nullptr, join_up = nullptr, join_pl = nullptr, join_dn = nullptr;
     cudaEvent_t t_fork = nullptr, t_up = nullptr, t_pl = nullptr, t_k = nullptr, t_dn = nullptr;  // phase timing of the last step
     bool timed = false;
-    cudaEvent_t landed[kMaxChunks] = {};  // own upload chunks (interprocess events, also waited on locally)
-    cudaEvent_t pulled = nullptr;         // own "pulls of this step are done" (interprocess)
+    cudaEvent_t landed[kMaxChunks] = {};  // own upload chunks
+    cudaEvent_t pulled = nullptr;         // own "pulls of this step are done"
     std::vector<cudaEvent_t> op_ev, k_ev;  // local: after each pull op / each kernel chunk
     PeerShm *shm = nullptr;
     char shm_name[64] = "";
@@ -193,12 +190,11 @@ int aai_peer_create(const aai_plan *plan, int32_t dtype, int32_t channels, int r
     for (cudaEvent_t *ev : {&g->fork, &g->join_up, &g->join_pl, &g->join_dn})
         ok(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     for (cudaEvent_t *ev : {&g->t_fork, &g->t_up, &g->t_pl, &g->t_k, &g->t_dn}) ok(cudaEventCreate(ev));
-    for (int c = 0; c < kMaxChunks; ++c)
-        ok(cudaEventCreateWithFlags(&g->landed[c], cudaEventDisableTiming | cudaEventInterprocess));
-    ok(cudaEventCreateWithFlags(&g->pulled, cudaEventDisableTiming | cudaEventInterprocess));
+    for (int c = 0; c < kMaxChunks; ++c) ok(cudaEventCreateWithFlags(&g->landed[c], cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&g->pulled, cudaEventDisableTiming));
     if (e != cudaSuccess) {
         aai_peer_destroy(g);
-        return fail(e, "aai_peer_create: streams / interprocess events");
+        return fail(e, "aai_peer_create: streams / events");
     }
     // the page of host counters the other ranks poll
     static std::atomic<unsigned> serial{0};
@@ -219,8 +215,8 @@ int aai_peer_create(const aai_plan *plan, int32_t dtype, int32_t channels, int r
         return AAI_ERR_CUDA;
     }
     g->shm = new (m) PeerShm();
-    g->shm->up_issued.store(0);
-    g->shm->pull_issued.store(0);
+    g->shm->landed.store(0);
+    g->shm->pulled.store(0);
     *out = g;
     return AAI_OK;
 }
@@ -238,8 +234,6 @@ int aai_peer_export(aai_peer *g, unsigned char blob[AAI_PEER_BLOB_BYTES]) {
     b.n_chunks = chunk_count(y1 - y0, g->plan.src_w * g->channels * (int64_t)elem_size(g->dtype));
     b.pitch = g->full.pitch_bytes;
     PEER_CUDA(cudaIpcGetMemHandle(&b.mem, g->full.data));
-    for (int c = 0; c < kMaxChunks; ++c) PEER_CUDA(cudaIpcGetEventHandle(&b.landed[c], g->landed[c]));
-    PEER_CUDA(cudaIpcGetEventHandle(&b.pulled, g->pulled));
     std::memcpy(b.shm_name, g->shm_name, sizeof b.shm_name);
     std::memset(blob, 0, AAI_PEER_BLOB_BYTES);
     std::memcpy(blob, &b, sizeof b);
@@ -271,8 +265,6 @@ int aai_peer_connect(aai_peer *g, const unsigned char *blobs) {
             continue;
         }
         PEER_CUDA(cudaIpcOpenMemHandle(&r.full, b.mem, cudaIpcMemLazyEnablePeerAccess));
-        for (int c = 0; c < kMaxChunks; ++c) PEER_CUDA(cudaIpcOpenEventHandle(&r.landed[c], b.landed[c]));
-        PEER_CUDA(cudaIpcOpenEventHandle(&r.pulled, b.pulled));
         const int fd = shm_open(b.shm_name, O_RDWR, 0600);
         void *m = fd >= 0 ? mmap(nullptr, 4096, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0) : MAP_FAILED;
         if (fd >= 0) close(fd);
@@ -343,22 +335,20 @@ int aai_peer_run(aai_peer *g, int mode, int arith, const aai_image *hsrc, const 
     cudaStream_t st = stream ? (cudaStream_t)stream : g->own;
     // fork: the internal streams start after everything already queued on the caller's stream (in particular after the
     // previous step of this group, which joined back into it: its kernels no longer read the device image)
-    PEER_CUDA(cudaEventRecord(g->fork, st));
     PEER_CUDA(cudaEventRecord(g->t_fork, st));
+    PEER_CUDA(cudaEventRecord(g->fork, st));
     for (cudaStream_t q : {g->up, g->pl, g->dn}) PEER_CUDA(cudaStreamWaitEvent(q, g->fork, 0));
 
     // 1. my rows may be overwritten once every reader has finished pulling them in the previous step
     if (s > 1)
         for (int p = 0; p < g->world; ++p) {
             if (p == g->rank) continue;
-            Remote &r = g->remote[(size_t)p];
-            if (!host_wait(r.shm->pull_issued, s - 1)) {
-                aai_set_error("aai_peer_run: rank %d did not finish enqueueing step %llu", p, (unsigned long long)(s - 1));
+            if (!host_wait(g->remote[(size_t)p].shm->pulled, s - 1)) {
+                aai_set_error("aai_peer_run: rank %d did not complete step %llu", p, (unsigned long long)(s - 1));
                 return AAI_ERR_CUDA;
             }
-            PEER_CUDA(cudaStreamWaitEvent(g->up, r.pulled, 0));
         }
-    // 2. upload my rows, chunk by chunk; each chunk re-records its interprocess event
+    // 2. upload my rows, chunk by chunk, an event after each
     const Remote &me = g->remote[(size_t)g->rank];
     for (int c = 0; c < me.n_chunks; ++c) {
         int64_t a, b;
@@ -370,55 +360,77 @@ int aai_peer_run(aai_peer *g, int mode, int arith, const aai_image *hsrc, const 
         PEER_CUDA(cudaEventRecord(g->landed[c], g->up));
     }
     PEER_CUDA(cudaEventRecord(g->t_up, g->up));
-    g->shm->up_issued.store(s, std::memory_order_release);
 
-    // 3. pull the rows of my halo that others own, chunk-major (round robin over the owners, so that the pulls track
-    //    the concurrent uploads); remember after which op each source row range is complete
+    // 3. progress loop (host driven): publish my chunks as they land; enqueue the pull of every chunk of my halo that
+    //    other ranks own the moment its owner has published it.  Remember after which op each source row range is complete.
     struct Op {
         int64_t a, b;   // source rows this op completes
-        int own_chunk;  // >= 0: one of my own upload chunks (no copy, the kernel waits on its event); -1: a pull
+        int own_chunk;  // >= 0: one of my own upload chunks (no copy, the kernel waits on its event); < 0: pull -1 - index
     };
     std::vector<Op> ops;
-    for (int p = 0; p < g->world; ++p) {
-        if (p == g->rank) continue;
-        const Remote &r = g->remote[(size_t)p];
-        if (std::max(r.y0, g->halo_y0) >= std::min(r.y1, g->halo_y1)) continue;
-        if (!host_wait(r.shm->up_issued, s)) {
-            aai_set_error("aai_peer_run: rank %d did not enter step %llu", p, (unsigned long long)s);
-            return AAI_ERR_CUDA;
-        }
+    std::vector<int> next((size_t)g->world, 0);  // next chunk of owner p to pull
+    for (int c = 0; c < me.n_chunks; ++c) {      // my own rows inside my halo: the kernels wait on the upload events
+        int64_t a, b;
+        chunk_rows(oy0, oy1, me.n_chunks, c, a, b);
+        a = std::max(a, g->halo_y0);
+        b = std::min(b, g->halo_y1);
+        if (b > a) ops.push_back({a, b, c});
     }
     size_t n_pull = 0;
-    for (int c = 0; c < kMaxChunks; ++c)
+    int published = 0, remaining = 0;
+    for (int p = 0; p < g->world; ++p) {
+        const Remote &r = g->remote[(size_t)p];
+        if (p == g->rank || std::max(r.y0, g->halo_y0) >= std::min(r.y1, g->halo_y1)) next[(size_t)p] = r.n_chunks;
+        remaining += r.n_chunks - next[(size_t)p];
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spin = 0; published < me.n_chunks || remaining > 0; ++spin) {
+        bool progressed = false;
+        while (published < me.n_chunks) {
+            const cudaError_t q = cudaEventQuery(g->landed[published]);
+            if (q == cudaErrorNotReady) break;
+            if (q != cudaSuccess) return fail(q, "aai_peer_run: upload");
+            ++published;
+            g->shm->landed.store((s - 1) * (uint64_t)me.n_chunks + (uint64_t)published, std::memory_order_release);
+            progressed = true;
+        }
         for (int p = 0; p < g->world; ++p) {
             const Remote &r = g->remote[(size_t)p];
-            if (c >= r.n_chunks) continue;
-            int64_t a, b;
-            chunk_rows(r.y0, r.y1, r.n_chunks, c, a, b);
-            a = std::max(a, g->halo_y0);
-            b = std::min(b, g->halo_y1);
-            if (b <= a) continue;
-            if (p == g->rank) {
-                ops.push_back({a, b, c});
-                continue;
+            while (next[(size_t)p] < r.n_chunks &&
+                   r.shm->landed.load(std::memory_order_acquire) >= (s - 1) * (uint64_t)r.n_chunks + (uint64_t)next[(size_t)p] + 1) {
+                const int c = next[(size_t)p]++;
+                --remaining;
+                progressed = true;
+                int64_t a, b;
+                chunk_rows(r.y0, r.y1, r.n_chunks, c, a, b);
+                a = std::max(a, g->halo_y0);
+                b = std::min(b, g->halo_y1);
+                if (b <= a) continue;
+                const int rc = copy_rows_2d((char *)g->full.data + a * g->full.pitch_bytes, g->full.pitch_bytes,
+                                            (const char *)r.full + a * g->full.pitch_bytes, g->full.pitch_bytes,
+                                            (size_t)row_bytes, b - a, cudaMemcpyDefault, g->pl);
+                if (rc != AAI_OK) return rc;
+                if (g->op_ev.size() <= n_pull) {
+                    cudaEvent_t e;
+                    PEER_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                    g->op_ev.push_back(e);
+                }
+                PEER_CUDA(cudaEventRecord(g->op_ev[n_pull], g->pl));
+                ops.push_back({a, b, -1 - (int)n_pull});
+                ++n_pull;
             }
-            PEER_CUDA(cudaStreamWaitEvent(g->pl, r.landed[c], 0));
-            const int rc = copy_rows_2d((char *)g->full.data + a * g->full.pitch_bytes, g->full.pitch_bytes,
-                                        (const char *)r.full + a * g->full.pitch_bytes, g->full.pitch_bytes,
-                                        (size_t)row_bytes, b - a, cudaMemcpyDefault, g->pl);
-            if (rc != AAI_OK) return rc;
-            if (g->op_ev.size() <= n_pull) {
-                cudaEvent_t e;
-                PEER_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-                g->op_ev.push_back(e);
-            }
-            PEER_CUDA(cudaEventRecord(g->op_ev[n_pull], g->pl));
-            ops.push_back({a, b, -1 - (int)n_pull});
-            ++n_pull;
         }
+        if (!progressed && (spin & 63) == 63) {
+            sched_yield();
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > kHostWaitSeconds) {
+                aai_set_error("aai_peer_run: step %llu timed out waiting for the uploads of the other ranks",
+                              (unsigned long long)s);
+                return AAI_ERR_CUDA;
+            }
+        }
+    }
     PEER_CUDA(cudaEventRecord(g->pulled, g->pl));
     PEER_CUDA(cudaEventRecord(g->t_pl, g->pl));
-    g->shm->pull_issued.store(s, std::memory_order_release);
 
     // 4. kernels + downloads, chunk by chunk, each kernel after the last op that completes a row range it reads
     const int64_t band_rows = g->row1 - g->row0;
@@ -452,6 +464,9 @@ int aai_peer_run(aai_peer *g, int mode, int arith, const aai_image *hsrc, const 
     PEER_CUDA(cudaEventRecord(g->t_k, st));
     PEER_CUDA(cudaEventRecord(g->t_dn, g->dn));
     g->timed = true;
+    // my pulls are complete: the owners may overwrite their rows (their next step waits for this counter)
+    PEER_CUDA(cudaEventSynchronize(g->pulled));
+    g->shm->pulled.store(s, std::memory_order_release);
     // join: the caller's stream continues after the uploads, the pulls and the downloads
     PEER_CUDA(cudaEventRecord(g->join_up, g->up));
     PEER_CUDA(cudaEventRecord(g->join_pl, g->pl));
@@ -482,9 +497,6 @@ int aai_peer_destroy(aai_peer *g) {
         Remote &r = g->remote[(size_t)p];
         if (p == g->rank) continue;
         if (r.full) cudaIpcCloseMemHandle(r.full);
-        for (cudaEvent_t e : r.landed)
-            if (e) cudaEventDestroy(e);
-        if (r.pulled) cudaEventDestroy(r.pulled);
         if (r.shm) munmap(r.shm, 4096);
     }
     for (cudaEvent_t e : g->landed)

@@ -437,8 +437,8 @@ class Bench:
                         peer.run(hsi, hdi, mode=mode, arith=arith, stream=stream, synchronize=False)
 
                     info["e2e_source"] = ("peer group (include/aai.h): every source row uploaded once by its owner rank in "
-                                          "chunks, halos pulled over NVLink as the chunks land (CUDA IPC peer copies, device-"
-                                          "side flags), kernel + download chunk-pipelined; no NCCL and no host barrier per step")
+                                          "chunks, halos pulled over NVLink as the chunks land (CUDA IPC peer copies, host-"
+                                          "driven shared-memory counters), kernel + download chunk-pipelined; no NCCL, no barrier")
                 else:
                     host_src = torch.empty((max(halo_rows, 1), W) + tail, dtype=t_dt, pin_memory=True)
                     host_src.copy_(dev_src)

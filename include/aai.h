@@ -217,11 +217,11 @@ int aai_run_host_batch(const aai_plan *plan, int mode, int arith, const aai_imag
  * for a rotated canvas, i.e. N/2 images over PCIe in total.  In a peer group every source row crosses PCIe exactly once:
  * rank r owns source rows [H r/N, H (r+1)/N), uploads them in chunks into its own full-size device image, and every
  * rank pulls the rows of its halo that it does not own out of the owners' device images with peer copies over NVLink
- * (CUDA IPC memory mappings) AS THE CHUNKS LAND: the device-side dependency "chunk c of owner p has arrived" is an
- * interprocess CUDA event (cudaIpcGetEventHandle) that the reader's copy stream waits on.  There is no NCCL and no
- * barrier per step; the host side only orders the *enqueueing* (a reader may only wait on an event once its owner has
- * re-recorded it for this step) through two counters per rank in a small POSIX shared-memory segment.  Kernel and
- * download of the band are chunk-pipelined behind the pulls, so a step costs about the slowest upload plus a short tail.
+ * (CUDA IPC memory mappings) AS THE CHUNKS LAND.  There is no NCCL and no barrier; the ranks synchronise through two
+ * monotonic counters per rank in a small POSIX shared-memory segment ("upload chunks landed", "steps whose pulls are
+ * complete"), driven by the calling host thread: it polls its own upload events and publishes them, polls the owners'
+ * counters and enqueues each pull the moment its chunk has landed.  Kernel and download of the band are chunk-pipelined
+ * behind the pulls on the caller's stream, so a step costs about the slowest upload plus a short tail.
  *
  * Set-up (once per plan / image type): every rank calls aai_peer_create, exchanges the AAI_PEER_BLOB_BYTES blob of
  * aai_peer_export with all ranks through ANY out-of-band channel (MPI, a torch.distributed object gather, files), and
@@ -230,8 +230,8 @@ int aai_run_host_batch(const aai_plan *plan, int mode, int arith, const aai_imag
 typedef struct aai_peer aai_peer;
 #define AAI_PEER_BLOB_BYTES 2048
 /* Tuning knob (process-wide, read by aai_peer_create; every rank must use the same value): into how many chunks an
- * owner cuts its upload, 1..8, default 4.  More chunks let the NVLink pulls start earlier, but every chunk costs each
- * reader one interprocess event wait.  Returns the value in force (n outside 1..8 only queries). */
+ * owner cuts its upload, 1..8, default 4 (more chunks let the NVLink pulls start earlier).  Returns the value in force
+ * (n outside 1..8 only queries). */
 int aai_peer_upload_chunks(int n);
 int aai_peer_create(const aai_plan *plan, int32_t dtype, int32_t channels, int rank, int world_size, int device,
                     aai_peer **out);
@@ -242,8 +242,9 @@ int aai_peer_owned_rows(const aai_peer *peer, int64_t *y0, int64_t *y1);
 int aai_peer_band(const aai_peer *peer, int64_t *row0, int64_t *row1);
 /* One step: `host_src` holds (at least) the owned source rows, `host_dst` receives the band's canvas rows (each may be
  * a band view: y0/rows).  Enqueued on `stream` (NULL = an internal stream, blocking); returns without waiting unless
- * `synchronize`.  All ranks must call it the same number of times; a rank waits (on the host, bounded) until the ranks
- * it exchanges rows with have entered the same step. */
+ * `synchronize`; it does return only after this rank's uploads have landed and its halo pulls have been enqueued and
+ * completed (the host drives that exchange), while its kernels and downloads may still be in flight on `stream`.  All
+ * ranks must call it the same number of times; waiting for a rank that never arrives fails after 60 s. */
 int aai_peer_run(aai_peer *peer, int mode, int arith, const aai_image *host_src, const aai_image *host_dst,
                  void *stream, int synchronize);
 /* The rank's full-size device source image (rows of the band's halo are valid after a step) -- for device-resident
