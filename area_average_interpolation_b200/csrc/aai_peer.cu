@@ -68,7 +68,7 @@ struct aai_peer {
     aai_image full{};                    // own device image (all rows allocated)
     aai_image band{};                    // device canvas band (allocated by the first step)
     cudaStream_t own = nullptr, up = nullptr, pl = nullptr, dn = nullptr;
-    cudaEvent_t fork = nullptr, join_up = nullptr, join_pl = nullptr, join_dn = nullptr;
+    cudaEvent_t fork = nullptr, join_up = nullptr, join_pl = nullptr, join_dn = nullptr, k_last = nullptr;
     cudaEvent_t t_fork = nullptr, t_up = nullptr, t_pl = nullptr, t_k = nullptr, t_dn = nullptr;  // phase timing of the last step
     bool timed = false;
     cudaEvent_t landed[kMaxChunks] = {};  // own upload chunks
@@ -187,7 +187,7 @@ int aai_peer_create(const aai_plan *plan, int32_t dtype, int32_t channels, int r
     ok(cudaStreamCreateWithFlags(&g->up, cudaStreamNonBlocking));
     ok(cudaStreamCreateWithFlags(&g->pl, cudaStreamNonBlocking));
     ok(cudaStreamCreateWithFlags(&g->dn, cudaStreamNonBlocking));
-    for (cudaEvent_t *ev : {&g->fork, &g->join_up, &g->join_pl, &g->join_dn})
+    for (cudaEvent_t *ev : {&g->fork, &g->join_up, &g->join_pl, &g->join_dn, &g->k_last})
         ok(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     for (cudaEvent_t *ev : {&g->t_fork, &g->t_up, &g->t_pl, &g->t_k, &g->t_dn}) ok(cudaEventCreate(ev));
     for (int c = 0; c < kMaxChunks; ++c) ok(cudaEventCreateWithFlags(&g->landed[c], cudaEventDisableTiming));
@@ -333,11 +333,17 @@ int aai_peer_run(aai_peer *g, int mode, int arith, const aai_image *hsrc, const 
     }
     const uint64_t s = ++g->step;
     cudaStream_t st = stream ? (cudaStream_t)stream : g->own;
-    // fork: the internal streams start after everything already queued on the caller's stream (in particular after the
-    // previous step of this group, which joined back into it: its kernels no longer read the device image)
-    PEER_CUDA(cudaEventRecord(g->t_fork, st));
-    PEER_CUDA(cudaEventRecord(g->fork, st));
-    for (cudaStream_t q : {g->up, g->pl, g->dn}) PEER_CUDA(cudaStreamWaitEvent(q, g->fork, 0));
+    // The copy streams start as soon as the previous step's KERNELS have finished (they were the last readers of the
+    // device image) -- not after its downloads: PCIe is full duplex, so this step's uploads overlap the previous step's
+    // device-to-host copies.  (Host buffers are read / written when the copies execute; the caller's stream orders only
+    // the kernels and the completion of `host_dst`.)  The first step starts after everything queued on the caller's stream.
+    if (s == 1) {
+        PEER_CUDA(cudaEventRecord(g->fork, st));
+        for (cudaStream_t q : {g->up, g->pl}) PEER_CUDA(cudaStreamWaitEvent(q, g->fork, 0));
+    } else {
+        for (cudaStream_t q : {g->up, g->pl}) PEER_CUDA(cudaStreamWaitEvent(q, g->k_last, 0));
+    }
+    PEER_CUDA(cudaEventRecord(g->t_fork, g->up));  // phase times count from the moment this step's upload may start
 
     // 1. my rows may be overwritten once every reader has finished pulling them in the previous step
     if (s > 1)
@@ -462,6 +468,7 @@ int aai_peer_run(aai_peer *g, int mode, int arith, const aai_image *hsrc, const 
         if (rc2 != AAI_OK) return rc2;
     }
     PEER_CUDA(cudaEventRecord(g->t_k, st));
+    PEER_CUDA(cudaEventRecord(g->k_last, st));
     PEER_CUDA(cudaEventRecord(g->t_dn, g->dn));
     g->timed = true;
     // my pulls are complete: the owners may overwrite their rows (their next step waits for this counter)
@@ -504,7 +511,7 @@ int aai_peer_destroy(aai_peer *g) {
     if (g->pulled) cudaEventDestroy(g->pulled);
     for (cudaEvent_t e : g->op_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : g->k_ev) cudaEventDestroy(e);
-    for (cudaEvent_t e : {g->fork, g->join_up, g->join_pl, g->join_dn, g->t_fork, g->t_up, g->t_pl, g->t_k, g->t_dn})
+    for (cudaEvent_t e : {g->fork, g->join_up, g->join_pl, g->join_dn, g->k_last, g->t_fork, g->t_up, g->t_pl, g->t_k, g->t_dn})
         if (e) cudaEventDestroy(e);
     for (cudaStream_t q : {g->own, g->up, g->pl, g->dn})
         if (q) cudaStreamDestroy(q);

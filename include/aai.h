@@ -241,7 +241,8 @@ int aai_peer_connect(aai_peer *peer, const unsigned char *blobs_of_all_ranks);
 int aai_peer_owned_rows(const aai_peer *peer, int64_t *y0, int64_t *y1);
 int aai_peer_band(const aai_peer *peer, int64_t *row0, int64_t *row1);
 /* One step: `host_src` holds (at least) the owned source rows, `host_dst` receives the band's canvas rows (each may be
- * a band view: y0/rows).  Enqueued on `stream` (NULL = an internal stream, blocking); returns without waiting unless
+ * a band view: y0/rows).  The host buffers are read / written when the copies execute: `host_src` must be ready when the
+ * call is made (a step's uploads overlap the previous step's downloads), `host_dst` is complete when `stream` is.  Enqueued on `stream` (NULL = an internal stream, blocking); returns without waiting unless
  * `synchronize`; it does return only after this rank's uploads have landed and its halo pulls have been enqueued and
  * completed (the host drives that exchange), while its kernels and downloads may still be in flight on `stream`.  All
  * ranks must call it the same number of times; waiting for a rank that never arrives fails after 60 s. */
@@ -250,7 +251,7 @@ int aai_peer_run(aai_peer *peer, int mode, int arith, const aai_image *host_src,
 /* The rank's full-size device source image (rows of the band's halo are valid after a step) -- for device-resident
  * follow-up work (aai_run_device). */
 int aai_peer_device_source(const aai_peer *peer, aai_image *out);
-/* Device-side phase times [ms] of this rank's LAST step, measured from the start of the step: own upload complete, last
+/* Device-side phase times [ms] of this rank's LAST step, measured from the start of its upload: own upload complete, last
  * halo pull complete, last kernel complete, last download complete (waits for the step to finish). */
 int aai_peer_last_timing(aai_peer *peer, float ms[4]);
 /* Frees the group's device memory and IPC mappings.  Call it once every rank has completed its last step (any barrier
