@@ -255,7 +255,10 @@ class Bench:
         self.numa = bind_to_gpu_numa_node(torch, self.local) if self.world > 1 else None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
-        self.stream = torch.cuda.current_stream().cuda_stream
+        # a real (non-default) stream for everything: the C ABI treats stream 0 as "use an internal stream and block"
+        self.tstream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.set_stream(self.tstream)
+        self.stream = self.tstream.cuda_stream
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
