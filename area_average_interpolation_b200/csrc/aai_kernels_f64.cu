@@ -23,7 +23,7 @@ namespace {
 
 constexpr int MAXN = AAI_MAXN;
 #ifndef AAI_F64_COOP
-#define AAI_F64_COOP 1  // border pixels warp-cooperative (0: each lane alone, the round-1 form; A/B in profiles/README.md)
+#define AAI_F64_COOP 0  // 1: border pixels warp-cooperative as in the FP32 kernel.  Measured on BASELINE config 4: 3.603 ms against 3.351 ms for each lane alone (profiles/README.md) -- the FP64 kernel keeps the round-1 form
 #endif
 
 template <typename TI, typename TO, int NC, bool IDENT>
