@@ -578,6 +578,9 @@ cudaError_t launch1(const AaiKernelParams &kp, int dst_dtype, cudaStream_t strea
 // (pixel_fast_f64, the reference's own centre expression).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int NF = MAXN - 1;
+#ifndef AAI_FAST_PRED_LOADS
+#define AAI_FAST_PRED_LOADS 1  // 0: all NF x NF candidates loaded up front (A/B in profiles/README.md)
+#endif
 template <typename TI, typename TO, int NC, bool IDENT, bool STAGED>
 __device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char *stage, int spitch, int sox, int soy) {
     static_assert(!STAGED || IDENT, "staging is implemented for identity addressing");
@@ -636,6 +639,38 @@ __device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char 
             }
         }
         const float rx0 = (float)(bx0 - irx) - fx, ry0 = (float)(by0 - iry) - fy;
+#if AAI_FAST_PRED_LOADS
+        // margins of all candidates first, then ONLY the inside cells are loaded (predicated LDG): a rotated warp-wide
+        // load touches one 32-byte sector per active lane, and less than half of the NF x NF candidates lie inside
+        float mm[NF][NF];
+#pragma unroll
+        for (int r = 0; r < NF; ++r) {
+            const float ry = ry0 + (float)r;
+            const float ur = -ry * g.sn, vr = ry * g.cs;
+#pragma unroll
+            for (int k = 0; k < NF; ++k) {
+                const float rx = rx0 + (float)k;
+                const float mu = g.half - fabsf(fmaf(rx, g.cs, ur));
+                const float mv = g.half - fabsf(fmaf(rx, g.sn, vr));
+                const float m = fminf(mu, mv);
+                worst = fminf(worst, fabsf(m));
+                mm[r][k] = m;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NF; ++r) {
+            const char *rowp = (STAGED ? stage : (const char *)kp.src) + roff[r];
+#pragma unroll
+            for (int k = 0; k < NF; ++k) {
+                if (mm[r][k] >= 0.0f) {  // closed point-in-square (837-864)
+                    count += 1.0f;
+#pragma unroll
+                    for (int ch = 0; ch < NC; ++ch)
+                        acc[ch] += LoadS<TI, STAGED>::get(rowp + coff[k] + ch * (int)sizeof(TI));
+                }
+            }
+        }
+#else
 #pragma unroll
         for (int r = 0; r < NF; ++r) {
             float v[NF][NC];
@@ -660,6 +695,7 @@ __device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char 
                 }
             }
         }
+#endif
     }
     if (!inside_img || worst < tau) {  // border pixel, or a centre within the guard band of a footprint edge: FP64 decides
         int c64;
