@@ -579,7 +579,7 @@ cudaError_t launch1(const AaiKernelParams &kp, int dst_dtype, cudaStream_t strea
 // ------------------------------------------------------------------------------------------------------------
 constexpr int NF = MAXN - 1;
 #ifndef AAI_FAST_PRED_LOADS
-#define AAI_FAST_PRED_LOADS 1  // 0: all NF x NF candidates loaded up front (A/B in profiles/README.md)
+#define AAI_FAST_PRED_LOADS 1  // multi-channel images: load only the inside cells (0: always load all candidates up front)
 #endif
 template <typename TI, typename TO, int NC, bool IDENT, bool STAGED>
 __device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char *stage, int spitch, int sox, int soy) {
@@ -639,9 +639,12 @@ __device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char 
             }
         }
         const float rx0 = (float)(bx0 - irx) - fx, ry0 = (float)(by0 - iry) - fy;
-#if AAI_FAST_PRED_LOADS
-        // margins of all candidates first, then ONLY the inside cells are loaded (predicated LDG): a rotated warp-wide
-        // load touches one 32-byte sector per active lane, and less than half of the NF x NF candidates lie inside
+        // Single channel: all NF x NF candidates are loaded up front (loads in flight while the margins are computed).
+        // Several channels: margins of all candidates first, then ONLY the inside cells are loaded (predicated LDG; less
+        // than half of the candidates lie inside, and three loads per candidate weigh more than their latency).  Measured
+        // (profiles/r2_n_fast_ab.txt): config 4 (1 channel) 0.615 ms up front vs 0.697 ms predicated; config 3 (RGB)
+        // 3.73 ms up front vs 3.21 ms predicated.
+        if constexpr (AAI_FAST_PRED_LOADS && NC > 1) {
         float mm[NF][NF];
 #pragma unroll
         for (int r = 0; r < NF; ++r) {
@@ -670,7 +673,7 @@ __device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char 
                 }
             }
         }
-#else
+        } else {
 #pragma unroll
         for (int r = 0; r < NF; ++r) {
             float v[NF][NC];
@@ -695,7 +698,7 @@ __device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char 
                 }
             }
         }
-#endif
+        }
     }
     if (!inside_img || worst < tau) {  // border pixel, or a centre within the guard band of a footprint edge: FP64 decides
         int c64;

@@ -56,6 +56,13 @@ CASES = [
     ("fast_17_45deg", 32, 32, "float64", 1.0, 1.7, (15.5, 15.5), 45.0, 2),
     ("fast_half_0deg", 64, 64, "float64", 1.0, 0.5, (32.0, 32.0), 0.0, 2),
     ("fast_q2_200deg", 50, 70, "float64", 1.0, 0.37, (25.0, 35.0), 200.0, 2),
+    # round 2: more structured degenerate inputs (appended, so that the seeds of the cases above do not move), compared
+    # under the conditioning mask like the two above
+    ("degenerate_45deg_integer_iso_upscale", 48, 48, "float64", 1.0, 1.7, (24.0, 24.0), 45.0, 1),  # cfg3's shape, lattice iso
+    ("degenerate_45deg_integer_iso_rect", 72, 40, "float64", 1.0, 0.37, (36.0, 20.0), 45.0, 1),
+    ("degenerate_30deg_half_iso_rect", 80, 56, "float64", 1.0, 0.5, (39.5, 27.5), 30.0, 1),   # L = 2
+    ("degenerate_135deg_integer_iso", 64, 64, "float64", 1.0, 0.5, (32.0, 32.0), 135.0, 1),    # quadrant 1 + exact 45 deg
+    ("degenerate_60deg_half_iso_fast", 60, 60, "float64", 1.0, 0.37, (29.5, 29.5), 60.0, 2),   # fast mode: centres on edges
 ]
 
 # validation failures: (name, w, h, src_res, dst_res) -> message

@@ -127,6 +127,31 @@ def test_no_cpu_fallback_without_a_gpu(aai):
     assert ei.value.status in (aai.ERR_NO_DEVICE, aai.ERR_CUDA)
 
 
+def test_peer_group_and_host_batch_fail_loudly_without_a_gpu(aai):
+    """The round-2 entry points (peer group, host batch) validate their arguments on the host and have no CPU fallback."""
+    import ctypes as C
+
+    assert aai.peer_upload_chunks(0) == 4 and aai.peer_upload_chunks(99) == 4  # out of range only queries
+    assert aai.peer_upload_chunks(2) == 2 and aai.peer_upload_chunks(4) == 4
+    plan = aai.make_plan(64, 64, 1.0, 0.5, (32, 32), 10.0)
+    h = C.c_void_p()
+    assert aai.lib().aai_peer_create(C.byref(plan), 7, 1, 0, 1, 0, C.byref(h)) == aai.ERR_ARGUMENT  # bad dtype
+    assert aai.lib().aai_peer_create(C.byref(plan), aai.F32, 1, 3, 2, 0, C.byref(h)) == aai.ERR_ARGUMENT  # rank >= world
+    bad = aai.make_plan(64, 64, 1.0, -1.0, (32, 32), 10.0)
+    assert aai.lib().aai_peer_create(C.byref(bad), aai.F32, 1, 0, 1, 0, C.byref(h)) == aai.ERR_RESOLUTION_NONPOS
+    if aai.device_count() > 0:
+        return
+    with pytest.raises(aai.AaiError) as ei:
+        aai.PeerGroup(plan, aai.F32, 1, 0, 1, 0, lambda b: [b])
+    assert ei.value.status in (aai.ERR_NO_DEVICE, aai.ERR_CUDA)
+    src = np.zeros((64, 64), dtype=np.float32)
+    dst = np.zeros((plan.dst_h, plan.dst_w), dtype=np.float32)
+    with pytest.raises(aai.AaiError) as ei:
+        aai.run_host_batch(plan, [aai._host_image(src)], [aai._host_image(dst)])
+    assert ei.value.status in (aai.ERR_NO_DEVICE, aai.ERR_CUDA, aai.ERR_ARGUMENT)
+    assert "no CPU fallback" in ei.value.message or ei.value.status != aai.ERR_ARGUMENT
+
+
 def test_partition_and_halo_properties_on_random_plans(aai):
     """Host logic of SURVEY 8e on random geometry (all quadrants, up- and downscaling, off-centre isocentres):
     bands tile the canvas, loads add up, a band's halo contains the halo of every sub-band (what the chunk-pipelined
