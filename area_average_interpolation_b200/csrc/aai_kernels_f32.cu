@@ -578,12 +578,21 @@ cudaError_t launch1(const AaiKernelParams &kp, int dst_dtype, cudaStream_t strea
 // (pixel_fast_f64, the reference's own centre expression).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int NF = MAXN - 1;
+#ifndef AAI_FAST_VEC_LOADS
+#define AAI_FAST_VEC_LOADS 1  // float, 1 channel, identity addressing: 128-bit loads (0: scalar loads; A/B in profiles/)
+#endif
 #ifndef AAI_FAST_PRED_LOADS
 #define AAI_FAST_PRED_LOADS 1  // multi-channel images: load only the inside cells (0: always load all candidates up front)
 #endif
-template <typename TI, typename TO, int NC, bool IDENT, bool STAGED>
+// VEC (float images, one channel, identity addressing, 16-byte aligned rows): the NF candidates of a row are read as
+// aligned 128-bit vectors (the 4 NV floats from the 16-byte boundary below the first candidate) and shifted into place
+// with selects -- 8 instead of 16 loads per pixel.  A rotated warp-wide load touches one 32-byte sector per lane whatever
+// its width, and the L1 tag stage is what bounds this kernel (l1tex 77 % with scalar loads).
+template <typename TI, typename TO, int NC, bool IDENT, bool STAGED, bool VEC = false>
 __device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char *stage, int spitch, int sox, int soy) {
     static_assert(!STAGED || IDENT, "staging is implemented for identity addressing");
+    static_assert(!VEC || (IDENT && !STAGED && NC == 1 && sizeof(TI) == 4), "vector loads: float, 1 channel, identity");
+    constexpr int NV = (NF + 3 + 3) / 4;  // aligned float4 vectors that cover NF floats from any offset 0..3
     const int x = blockIdx.x * TILE_W + threadIdx.x;
     const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
     if (x >= kp.dst_w || y >= kp.row1) return;
@@ -604,8 +613,9 @@ __device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char 
         return;
     }
     // the unrolled NF x NF block starts at (bx0, by0); it must lie inside the image (else: FP64 path below)
+    // (VEC: the aligned vectors must end inside the row as well)
     const bool inside_img = bx0 >= 0 && by0 >= 0 && bx0 + NF - 1 <= kp.mod_w - 1 && by0 + NF - 1 <= kp.mod_h - 1 &&
-                            bx1 - bx0 < NF && by1 - by0 < NF;
+                            bx1 - bx0 < NF && by1 - by0 < NF && (!VEC || (bx0 & ~3) + 4 * NV <= kp.mod_w);
     float count = 0.0f, acc[NC], worst = 1.0f;
 #pragma unroll
     for (int ch = 0; ch < NC; ++ch) acc[ch] = 0.0f;
@@ -639,6 +649,47 @@ __device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char 
             }
         }
         const float rx0 = (float)(bx0 - irx) - fx, ry0 = (float)(by0 - iry) - fy;
+        if constexpr (VEC) {
+            const int o = bx0 & 3;
+            const char *rowp = (const char *)kp.src + (int64_t)(by0 - src_row0(kp)) * kp.src_pitch + (int64_t)(bx0 - o) * 4;
+            float v[NF][NF];
+#pragma unroll
+            for (int r = 0; r < NF; ++r) {  // all vector loads first: NF * NV independent 128-bit loads in flight
+                float w[4 * NV];
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const float4 t = __ldg(reinterpret_cast<const float4 *>(rowp) + q);
+                    w[4 * q] = t.x;
+                    w[4 * q + 1] = t.y;
+                    w[4 * q + 2] = t.z;
+                    w[4 * q + 3] = t.w;
+                }
+                rowp += kp.src_pitch;
+                // shift by o = 0..3 in two select stages (o & 1, then o & 2)
+                float t1[NF + 2];
+#pragma unroll
+                for (int i = 0; i < NF + 2; ++i) t1[i] = (o & 1) ? w[i + 1] : w[i];
+#pragma unroll
+                for (int k = 0; k < NF; ++k) v[r][k] = (o & 2) ? t1[k + 2] : t1[k];
+            }
+#pragma unroll
+            for (int r = 0; r < NF; ++r) {
+                const float ry = ry0 + (float)r;
+                const float ur = -ry * g.sn, vr = ry * g.cs;
+#pragma unroll
+                for (int k = 0; k < NF; ++k) {
+                    const float rx = rx0 + (float)k;
+                    const float mu = g.half - fabsf(fmaf(rx, g.cs, ur));
+                    const float mv = g.half - fabsf(fmaf(rx, g.sn, vr));
+                    const float m = fminf(mu, mv);
+                    worst = fminf(worst, fabsf(m));
+                    if (m >= 0.0f) {  // closed point-in-square (837-864); predicated adds, no branch
+                        count += 1.0f;
+                        acc[0] += v[r][k];
+                    }
+                }
+            }
+        } else
         // Single channel: all NF x NF candidates are loaded up front (loads in flight while the margins are computed).
         // Several channels: margins of all candidates first, then ONLY the inside cells are loaded (predicated LDG; less
         // than half of the candidates lie inside, and three loads per candidate weigh more than their latency).  Measured
@@ -718,6 +769,12 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 1024 / (TILE_W * TILE_H))
     fast_kernel_f32u(const __grid_constant__ AaiKernelParams kp) {
     fast_body<TI, TO, NC, IDENT, false>(kp, nullptr, 0, 0, 0);
 }
+// float images, one channel, identity addressing, 16-byte aligned rows: 128-bit loads (see fast_body)
+template <typename TO>
+__global__ void __launch_bounds__(TILE_W *TILE_H, 1024 / (TILE_W * TILE_H))
+    fast_kernel_f32u_vec(const __grid_constant__ AaiKernelParams kp) {
+    fast_body<float, TO, 1, true, false, true>(kp, nullptr, 0, 0, 0);
+}
 
 // the same kernel with the CTA's source window staged through shared memory by TMA (AAI_ARITH_F32_STAGED).  Measured on
 // BASELINE config 4: 0.658 ms against 0.616 ms for the LDG kernel -- the L1 tag stage is relieved (77 % -> 42 %), but every
@@ -745,6 +802,12 @@ cudaError_t launch_fast3(const AaiKernelParams &kp, cudaStream_t stream) {
         if (kp.staged && stage_prepare<TI, NC>(kp, (double)kp.shapef.hb + 1e-5, h)) {  // A/B variant (AAI_ARITH_F32_STAGED)
             fast_kernel_f32u_tma<TI, TO, NC><<<grid, block, h.smem, stream>>>(h.map, kp, h.sp);
             return cudaGetLastError();
+        }
+        if constexpr (sizeof(TI) == 4 && NC == 1) {
+            if ((kp.src_pitch % 16) == 0 && (reinterpret_cast<uintptr_t>(kp.src) % 16) == 0 && AAI_FAST_VEC_LOADS) {
+                fast_kernel_f32u_vec<TO><<<grid, block, 0, stream>>>(kp);
+                return cudaGetLastError();
+            }
         }
         fast_kernel_f32u<TI, TO, NC, true><<<grid, block, 0, stream>>>(kp);
     } else {

@@ -515,11 +515,13 @@ cudaError_t launch_sep_src(const AaiKernelParams &kp, int src_dtype, int dst_dty
 // the expanded-frame index map (as in the FP32 overlap kernel), MAXT x MAXT loads per canvas pixel through L1.
 // (Before round 2 these cases ran on the FP64 direct-tap kernel with a division per tap.)
 // ------------------------------------------------------------------------------------------------------------
-template <typename TI, typename TO, int NC, int MAXT>
+// TRANSPOSED (quadrants 1 / 3: canvas y runs along source x): the lanes of a warp step along canvas y, so that the
+// MAXT x MAXT loads of a pixel stay coalesced and the one store per pixel takes the stride instead.
+template <typename TI, typename TO, int NC, int MAXT, bool TRANSPOSED>
 __global__ void __launch_bounds__(TILE_W *TILE_H)
     separable_direct_f32(const __grid_constant__ AaiKernelParams kp) {
-    const int x = blockIdx.x * TILE_W + threadIdx.x;
-    const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
+    const int x = TRANSPOSED ? blockIdx.x * TILE_H + threadIdx.y : blockIdx.x * TILE_W + threadIdx.x;
+    const int y = kp.row0 + (TRANSPOSED ? blockIdx.y * TILE_W + threadIdx.x : blockIdx.y * TILE_H + threadIdx.y);
     if (x >= kp.dst_w || y >= kp.row1) return;
     double cx, cy;
     pixel_centre(kp, x, y, cx, cy);
@@ -571,15 +573,22 @@ cudaError_t launch_direct_taps(const AaiKernelParams &kp, cudaStream_t stream) {
     const int taps = (int)ceil(L - 1e-12) + 1;
     const int rows = kp.row1 - kp.row0;
     dim3 block(TILE_W, TILE_H);
-    dim3 grid((kp.dst_w + TILE_W - 1) / TILE_W, (rows + TILE_H - 1) / TILE_H, kp.batch > 1 ? kp.batch : 1);
-    if (taps <= 3)
-        separable_direct_f32<TI, TO, NC, 3><<<grid, block, 0, stream>>>(kp);
-    else if (taps <= 4)
-        separable_direct_f32<TI, TO, NC, 4><<<grid, block, 0, stream>>>(kp);
-    else if (taps <= 6)
-        separable_direct_f32<TI, TO, NC, 6><<<grid, block, 0, stream>>>(kp);
-    else
+    const bool tr = kp.e_axi == 0;  // quadrants 1 / 3
+    const int tw = tr ? TILE_H : TILE_W, th = tr ? TILE_W : TILE_H;
+    if ((rows + th - 1) / th > 65535) return cudaErrorNotSupported;
+    dim3 grid((kp.dst_w + tw - 1) / tw, (rows + th - 1) / th, kp.batch > 1 ? kp.batch : 1);
+    if (taps <= 3) {
+        if (tr) separable_direct_f32<TI, TO, NC, 3, true><<<grid, block, 0, stream>>>(kp);
+        else separable_direct_f32<TI, TO, NC, 3, false><<<grid, block, 0, stream>>>(kp);
+    } else if (taps <= 4) {
+        if (tr) separable_direct_f32<TI, TO, NC, 4, true><<<grid, block, 0, stream>>>(kp);
+        else separable_direct_f32<TI, TO, NC, 4, false><<<grid, block, 0, stream>>>(kp);
+    } else if (taps <= 6) {
+        if (tr) separable_direct_f32<TI, TO, NC, 6, true><<<grid, block, 0, stream>>>(kp);
+        else separable_direct_f32<TI, TO, NC, 6, false><<<grid, block, 0, stream>>>(kp);
+    } else {
         return cudaErrorNotSupported;
+    }
     return cudaGetLastError();
 }
 template <typename TI, typename TO>
