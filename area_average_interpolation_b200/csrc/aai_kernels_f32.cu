@@ -578,9 +578,6 @@ cudaError_t launch1(const AaiKernelParams &kp, int dst_dtype, cudaStream_t strea
 // (pixel_fast_f64, the reference's own centre expression).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int NF = MAXN - 1;
-#ifndef AAI_FAST_SKEW
-#define AAI_FAST_SKEW 1  // identity addressing: lanes follow the staircase of constant source row (0: plain 16 x 8 tiles)
-#endif
 #ifndef AAI_FAST_VEC_LOADS
 #define AAI_FAST_VEC_LOADS 1  // float, 1 channel, identity addressing: 128-bit loads (0: scalar loads; A/B in profiles/)
 #endif
@@ -596,14 +593,9 @@ __device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char 
     static_assert(!STAGED || IDENT, "staging is implemented for identity addressing");
     static_assert(!VEC || (IDENT && !STAGED && NC == 1 && sizeof(TI) == 4), "vector loads: float, 1 channel, identity");
     constexpr int NV = (NF + 3 + 3) / 4;  // aligned float4 vectors that cover NF floats from any offset 0..3
-    // Skewed thread mapping (identity addressing): stepping one canvas pixel to the right and tan(theta) pixels down keeps
-    // the footprint centre in the SAME source row, so the lanes of a warp follow that staircase -- canvas row
-    // y = yb + floor(x tan) -- and a warp-wide load touches ~10 sectors of one or two source rows instead of 28 sectors of
-    // 13 rows (the L1 tag stage bounds this kernel).  (x, yb) <-> (x, y) is a bijection; rows outside the band are masked.
     const int x = blockIdx.x * TILE_W + threadIdx.x;
-    const int yb = kp.row0 - kp.skew_max + blockIdx.y * TILE_H + threadIdx.y;
-    const int y = yb + (int)(((int64_t)x * kp.skew_q16) >> 16);
-    if (x >= kp.dst_w || y < kp.row0 || y >= kp.row1) return;
+    const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
+    if (x >= kp.dst_w || y >= kp.row1) return;
     const double cx = fma((double)x, kp.aff_xx, fma((double)y, kp.aff_xy, kp.aff_x0));
     const double cy = fma((double)x, kp.aff_yx, fma((double)y, kp.aff_yy, kp.aff_y0));
     const int irx = __double2int_rn(cx), iry = __double2int_rn(cy);
@@ -805,26 +797,6 @@ cudaError_t launch_fast3(const AaiKernelParams &kp, cudaStream_t stream) {
     if (rows <= 0 || kp.dst_w <= 0) return cudaSuccess;
     dim3 block(TILE_W, TILE_H);
     dim3 grid((kp.dst_w + TILE_W - 1) / TILE_W, (rows + TILE_H - 1) / TILE_H, kp.batch > 1 ? kp.batch : 1);
-    if (kp.scale == 1 && kp.quadrant == 0 && !kp.staged && AAI_FAST_SKEW) {  // skewed thread mapping (see fast_body)
-        AaiKernelParams k2 = kp;
-        const double t = kp.shape.sn / kp.shape.cs;
-        if (t < 16.0) {
-            k2.skew_q16 = (int32_t)(t * 65536.0 + 0.5);
-            k2.skew_max = (int32_t)(((int64_t)(kp.dst_w - 1) * k2.skew_q16) >> 16);
-            const int64_t gy = ((int64_t)rows + k2.skew_max + TILE_H - 1) / TILE_H;
-            if (gy <= 65535) {
-                grid.y = (unsigned)gy;
-                if constexpr (sizeof(TI) == 4 && NC == 1) {
-                    if ((kp.src_pitch % 16) == 0 && (reinterpret_cast<uintptr_t>(kp.src) % 16) == 0 && AAI_FAST_VEC_LOADS) {
-                        fast_kernel_f32u_vec<TO><<<grid, block, 0, stream>>>(k2);
-                        return cudaGetLastError();
-                    }
-                }
-                fast_kernel_f32u<TI, TO, NC, true><<<grid, block, 0, stream>>>(k2);
-                return cudaGetLastError();
-            }
-        }
-    }
     if (kp.scale == 1 && kp.quadrant == 0) {
         StageHost h;
         if (kp.staged && stage_prepare<TI, NC>(kp, (double)kp.shapef.hb + 1e-5, h)) {  // A/B variant (AAI_ARITH_F32_STAGED)
