@@ -17,6 +17,8 @@ ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--arith", default="f64")
 ap.add_argument("--mode", type=int, default=1, help="1 area average, 2 fast mode")
 ap.add_argument("--dst", default="same", help="canvas element type: same (as the source) | float32")
+ap.add_argument("--angle", type=float, default=None, help="override the rotation angle of the config")
+ap.add_argument("--ratio", type=float, default=None, help="override the ratio of the config")
 ap.add_argument("--lib", default="", help="another build of libaai_b200.so (A/B variants)")
 ap.add_argument("--batch", type=int, default=0, help="config 5: slices per launch (aai_run_device_batch)")
 args = ap.parse_args()
@@ -24,7 +26,8 @@ cfg = CONFIGS[args.config]
 if args.lib:
     aai.LIB_PATH = args.lib
 dev = torch.device("cuda:0")
-plan = aai.make_plan(cfg["w"], cfg["h"], 1.0, cfg["ratio"], cfg["iso"], cfg["angle"])
+plan = aai.make_plan(cfg["w"], cfg["h"], 1.0, cfg["ratio"] if args.ratio is None else args.ratio, cfg["iso"],
+                     cfg["angle"] if args.angle is None else args.angle)
 tail = (cfg["ch"],) if cfg["ch"] > 1 else ()
 if cfg["dtype"] == "uint8":
     src = torch.randint(0, 256, (cfg["h"], cfg["w"]) + tail, dtype=torch.uint8, device=dev)
