@@ -220,14 +220,11 @@ bool stage_prepare(const AaiKernelParams &kp, double ext, StageHost &h) {
 //                 most 2 x 2 source pixels, so the four weights are computed DIRECTLY (aai_quadrant_areas_f32: Green form
 //                 about the corner of the source-pixel boundaries, no loop over cells), the quirk corrections are added
 //                 per source pixel, and each source pixel is loaded ONCE per canvas pixel
-//   ADDR_AFFINE   scale 1 with a quadrant pre-rotation (90 / 180 / 270 degrees and everything in between): expanded pixel
-//                 (i,j) -> source byte offset is affine, base + i cstep + j rstep, with signed strides (no division, no
-//                 per-axis selects: the general path costs 25-29 % more than ADDR_IDENT on config 4, this one ~5 %)
-enum { ADDR_GENERAL = 0, ADDR_IDENT = 1, ADDR_GROUPED = 2, ADDR_AFFINE = 3 };
+enum { ADDR_GENERAL = 0, ADDR_IDENT = 1, ADDR_GROUPED = 2 };
 // stage / spitch / sox / soy: the CTA's staged source window (STAGED only): row pitch in bytes, origin in elements / rows
 template <typename TI, typename TO, int NC, int ADDR, bool STAGED>
 __device__ __forceinline__ void overlap_body(const AaiKernelParams &kp, const char *stage, int spitch, int sox, int soy) {
-    constexpr bool IDENT = ADDR == ADDR_IDENT, GROUPED = ADDR == ADDR_GROUPED, AFFINE = ADDR == ADDR_AFFINE;
+    constexpr bool IDENT = ADDR == ADDR_IDENT, GROUPED = ADDR == ADDR_GROUPED;
     static_assert(!STAGED || IDENT, "staging is implemented for identity addressing");
     // (no early return: every lane of a warp reaches the cooperative FP64 section at the end)
     const int x = blockIdx.x * TILE_W + threadIdx.x;
@@ -294,17 +291,11 @@ __device__ __forceinline__ void overlap_body(const AaiKernelParams &kp, const ch
         auto div_s = [&](int e) -> int64_t {
             return (int64_t)(kp.scale != 1 ? __umulhi((unsigned)e, kp.div_magic) : (unsigned)e);
         };
-        // (AFFINE: scale 1, so the map is affine in (i, j) with signed byte strides)
-        const int64_t a_cstep = (int64_t)kp.e_ayi * kp.src_pitch + (int64_t)kp.e_axi * ESZ;
-        const int64_t a_rstep = (int64_t)kp.e_ayj * kp.src_pitch + (int64_t)kp.e_axj * ESZ;
-        const int64_t a_base = (int64_t)(kp.e_ay0 - src_row0(kp)) * kp.src_pitch + (int64_t)kp.e_ax0 * ESZ;
         auto col_off = [&](int i) -> int64_t {
-            if constexpr (AFFINE) return (int64_t)i * a_cstep;
             return swapped ? (div_s(kp.e_ayi * i + kp.e_ay0) - src_row0(kp)) * kp.src_pitch
                            : div_s(kp.e_axi * i + kp.e_ax0) * ESZ;
         };
         auto row_off = [&](int j) -> int64_t {
-            if constexpr (AFFINE) return a_base + (int64_t)j * a_rstep;
             return swapped ? div_s(kp.e_axj * j + kp.e_ax0) * ESZ
                            : (div_s(kp.e_ayj * j + kp.e_ay0) - src_row0(kp)) * kp.src_pitch;
         };
@@ -552,9 +543,7 @@ cudaError_t launch3(const AaiKernelParams &kp, cudaStream_t stream) {
             return cudaGetLastError();
         }
         overlap_kernel_f32<TI, TO, NC, ADDR_IDENT><<<grid, block, 0, stream>>>(kp);
-    } else if (kp.scale == 1)
-        overlap_kernel_f32<TI, TO, NC, ADDR_AFFINE><<<grid, block, 0, stream>>>(kp);
-    else if (MAXN == 4 && kp.scale >= MAXN - 1)
+    } else if (MAXN == 4 && kp.scale >= MAXN - 1)
         overlap_kernel_f32<TI, TO, NC, (MAXN == 4 ? ADDR_GROUPED : ADDR_GENERAL)><<<grid, block, 0, stream>>>(kp);
     else
         overlap_kernel_f32<TI, TO, NC, ADDR_GENERAL><<<grid, block, 0, stream>>>(kp);
@@ -653,16 +642,10 @@ __device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char 
 #pragma unroll
             for (int k = 0; k < NF; ++k) {
                 const int i = bx0 + k, j = by0 + k;
-                if (kp.scale == 1) {  // a quadrant pre-rotation only: affine, signed byte strides
-                    coff[k] = (int64_t)i * ((int64_t)kp.e_ayi * kp.src_pitch + (int64_t)kp.e_axi * ESZ);
-                    roff[k] = (int64_t)(kp.e_ay0 - src_row0(kp)) * kp.src_pitch + (int64_t)kp.e_ax0 * ESZ +
-                              (int64_t)j * ((int64_t)kp.e_ayj * kp.src_pitch + (int64_t)kp.e_axj * ESZ);
-                } else {
-                    coff[k] = swapped ? (div_s(kp.e_ayi * i + kp.e_ay0) - src_row0(kp)) * kp.src_pitch
-                                      : div_s(kp.e_axi * i + kp.e_ax0) * ESZ;
-                    roff[k] = swapped ? div_s(kp.e_axj * j + kp.e_ax0) * ESZ
-                                      : (div_s(kp.e_ayj * j + kp.e_ay0) - src_row0(kp)) * kp.src_pitch;
-                }
+                coff[k] = swapped ? (div_s(kp.e_ayi * i + kp.e_ay0) - src_row0(kp)) * kp.src_pitch
+                                  : div_s(kp.e_axi * i + kp.e_ax0) * ESZ;
+                roff[k] = swapped ? div_s(kp.e_axj * j + kp.e_ax0) * ESZ
+                                  : (div_s(kp.e_ayj * j + kp.e_ay0) - src_row0(kp)) * kp.src_pitch;
             }
         }
         const float rx0 = (float)(bx0 - irx) - fx, ry0 = (float)(by0 - iry) - fy;

@@ -88,18 +88,11 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 512 / (TILE_W *TILE_H))
         auto div_s = [&](int e) -> int64_t {
             return (int64_t)(kp.scale != 1 ? __umulhi((unsigned)e, kp.div_magic) : (unsigned)e);
         };
-        // (scale 1 with a quadrant pre-rotation: the map is affine with signed byte strides -- no division, no selects)
-        const bool affine = kp.scale == 1;
-        const int64_t a_cstep = (int64_t)kp.e_ayi * kp.src_pitch + (int64_t)kp.e_axi * ESZ;
-        const int64_t a_rstep = (int64_t)kp.e_ayj * kp.src_pitch + (int64_t)kp.e_axj * ESZ;
-        const int64_t a_base = (int64_t)(kp.e_ay0 - src_row0(kp)) * kp.src_pitch + (int64_t)kp.e_ax0 * ESZ;
         auto col_off = [&](int i) -> int64_t {
-            if (affine) return (int64_t)i * a_cstep;
             return swapped ? (div_s(kp.e_ayi * i + kp.e_ay0) - src_row0(kp)) * kp.src_pitch
                            : div_s(kp.e_axi * i + kp.e_ax0) * ESZ;
         };
         auto row_off = [&](int j) -> int64_t {
-            if (affine) return a_base + (int64_t)j * a_rstep;
             return swapped ? div_s(kp.e_axj * j + kp.e_ax0) * ESZ
                            : (div_s(kp.e_ayj * j + kp.e_ay0) - src_row0(kp)) * kp.src_pitch;
         };
