@@ -29,7 +29,8 @@ struct AaiKernelParams {
     AaiShapeF shapef; // the same in FP32 (+ guard band) for the FP32 kernel
     int32_t f32_ok;   // FP32 kernel admissible (angle not within ~3 degrees of an axis)
     int32_t quirk;    // 1: reproduce the reference's shape-2/4 leg quirk (default), 0: geometrically exact areas
-    int32_t staged;   // FP32 overlap kernel: 1 = source window staged through shared memory by TMA (A/B variant)
+    int32_t staged;   // FP32 kernels: 1 = source window staged through shared memory by TMA (A/B variant),
+                      // 2 = fast mode binned from the source side where aai_kernels_bin.cu applies (A/B variant)
     double reach;     // L*sqrt(2)/2 (search window, 426-429)
     double hb;        // h*(c+s): half extent of the footprint's axis-aligned bounding box
     int32_t mod_w, mod_h, dst_w, dst_h;
@@ -78,6 +79,8 @@ int aai_launch_fast_f32_n4(const AaiKernelParams &kp, int src_dtype, int dst_dty
 int aai_launch_fast_f32_n5(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_fast_f32_n6(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_fast_f32_n8(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
+// aai_kernels_bin.cu: fast mode by source-side binning; cudaErrorNotSupported when its preconditions do not hold
+int aai_launch_fast_bin(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
 // aai_kernels_f64.cu, likewise (unrolled FP64 kernel; cudaErrorNotSupported -> the rolled kernel in aai_kernels.cu)
 int aai_launch_overlap_f64_n4(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
 int aai_launch_overlap_f64_n5(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);

@@ -323,6 +323,10 @@ int aai_launch_fast(const AaiKernelParams &kp, int arith, int src_dtype, int dst
     const uint64_t max_e = (uint64_t)(kp.mod_w > kp.mod_h ? kp.mod_w : kp.mod_h);
     const bool f32 = arith == AAI_ARITH_F32 && src_dtype != AAI_F64 && dst_dtype != AAI_F64 && max_e < (1u << 30);
     // unrolled kernel: at most floor(2 hb + ~1e-5) + 1 lattice points per axis lie within hb of a footprint centre
+    if (f32 && kp.staged == 2) {  // AAI_ARITH_F32_BINNED: float single-channel images in the source frame
+        const int e = aai_launch_fast_bin(kp, src_dtype, dst_dtype, stream);
+        if (e != (int)cudaErrorNotSupported) return e;
+    }
     if (f32 && (kp.channels == 1 || kp.channels == 3) && max_e * (uint64_t)kp.scale < 0x100000000ULL) {
         const int nf = (int)floor(2.0 * ((double)kp.shapef.hb + 4e-6) + 1e-6) + 1;
         if (nf <= 3) return aai_launch_fast_f32_n4(kp, src_dtype, dst_dtype, stream);

@@ -68,7 +68,13 @@ enum {
      * lay-out BASELINE.json's north star describes).  Same results; measured slower / faster per shape in
      * profiles/README.md -- the default FP32 kernel reads through L1.  Identity addressing only (scale 1, quadrant 0);
      * otherwise identical to AAI_ARITH_F32. */
-    AAI_ARITH_F32_STAGED = 2
+    AAI_ARITH_F32_STAGED = 2,
+    /* AAI_ARITH_F32 with fast mode computed from the SOURCE side where that applies (float single-channel images, scale 1,
+     * quadrant 0, footprint box up to 5 pixels): every source pixel is read once, coalesced, and binned into the one
+     * footprint it lies in (aai_kernels_bin.cu).  Same inside decisions as the default canvas-side gather kernel, a
+     * different FP32 summation order; bitwise reproducible across band partitions.  Measured slower than the gather
+     * kernel on B200 (profiles/README.md), so it is not the default.  Identical to AAI_ARITH_F32 in the other modes. */
+    AAI_ARITH_F32_BINNED = 3
 };
 
 /*
