@@ -22,7 +22,7 @@ ERR_RESOLUTION_XY, ERR_RESOLUTION_NONPOS, ERR_NO_ROWS, ERR_NO_COLUMNS = 1, 2, 3,
 ERR_ANGLE, ERR_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE = 5, 6, 7, 8
 F64, F32, U8 = 0, 1, 2
 MODE_AREA_AVERAGE, MODE_FAST, MODE_AREA_AVERAGE_EXACT = 1, 2, 3
-ARITH_F64, ARITH_F32, ARITH_F32_STAGED, ARITH_F32_BINNED = 0, 1, 2, 3
+ARITH_F64, ARITH_F32, ARITH_F32_STAGED, ARITH_F32_BINNED, ARITH_F32_RING = 0, 1, 2, 3, 4
 
 _NP_TO_AAI = {np.dtype(np.float64): F64, np.dtype(np.float32): F32, np.dtype(np.uint8): U8}
 _AAI_TO_NP = {v: k for k, v in _NP_TO_AAI.items()}

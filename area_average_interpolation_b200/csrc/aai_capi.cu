@@ -174,7 +174,7 @@ AaiKernelParams aai_make_kernel_params(const aai_plan &p, const aai_image &src, 
 static int launch_rows(const aai_plan &plan, int mode, int arith, AaiKernelParams kp, int src_dtype, int dst_dtype,
                        void *stream) {
     const int32_t row0 = kp.row0, row1 = kp.row1;
-    kp.staged = arith == AAI_ARITH_F32_STAGED ? 1 : arith == AAI_ARITH_F32_BINNED ? 2 : 0;
+    kp.staged = arith == AAI_ARITH_F32_STAGED ? 1 : arith == AAI_ARITH_F32_BINNED ? 2 : arith == AAI_ARITH_F32_RING ? 3 : 0;
     if (kp.staged) arith = AAI_ARITH_F32;
     for (int64_t a = row0; a < row1; a += AAI_MAX_ROWS_PER_LAUNCH) {
         kp.row0 = (int32_t)a;
@@ -338,7 +338,8 @@ int aai_run_device(const aai_plan *plan, int mode, int arith, const aai_image *s
         aai_set_error("aai_run_device: interpolation mode must be 1, 2 or 3");
         return AAI_ERR_ARGUMENT;
     }
-    if (arith != AAI_ARITH_F64 && arith != AAI_ARITH_F32 && arith != AAI_ARITH_F32_STAGED && arith != AAI_ARITH_F32_BINNED) {
+    if (arith != AAI_ARITH_F64 && arith != AAI_ARITH_F32 && arith != AAI_ARITH_F32_STAGED && arith != AAI_ARITH_F32_BINNED &&
+        arith != AAI_ARITH_F32_RING) {
         aai_set_error("aai_run_device: unknown arithmetic %d", arith);
         return AAI_ERR_ARGUMENT;
     }
@@ -459,7 +460,7 @@ int aai_run_device_batch(const aai_plan *plan, int mode, int arith, const aai_im
                  d0.width == plan->dst_w && d0.height == plan->dst_h && s0.channels == d0.channels &&
                  (mode == AAI_MODE_AREA_AVERAGE || mode == AAI_MODE_FAST || mode == AAI_MODE_AREA_AVERAGE_EXACT) &&
                  (arith == AAI_ARITH_F64 || arith == AAI_ARITH_F32 || arith == AAI_ARITH_F32_STAGED ||
-                  arith == AAI_ARITH_F32_BINNED);
+                  arith == AAI_ARITH_F32_BINNED || arith == AAI_ARITH_F32_RING);
     const int64_t sstride = stack ? (const char *)srcs[1].data - (const char *)s0.data : 0;
     const int64_t dstride = stack ? (const char *)dsts[1].data - (const char *)d0.data : 0;
     for (int k = 1; stack && k < n_images; ++k) {

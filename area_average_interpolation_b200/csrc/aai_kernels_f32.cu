@@ -20,6 +20,7 @@
 //     (pixel_f64) -- FP32 rounding can never flip one of the reference's discontinuous decisions.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cmath>
 
 #include "aai_device.cuh"
@@ -538,7 +539,7 @@ cudaError_t launch3(const AaiKernelParams &kp, cudaStream_t stream) {
     dim3 grid((kp.dst_w + TILE_W - 1) / TILE_W, (rows + TILE_H - 1) / TILE_H, kp.batch > 1 ? kp.batch : 1);
     if (kp.scale == 1 && kp.quadrant == 0) {
         StageHost h;
-        if (kp.staged && stage_prepare<TI, NC>(kp, (double)kp.ext32, h)) {
+        if (kp.staged == 1 && stage_prepare<TI, NC>(kp, (double)kp.ext32, h)) {
             overlap_kernel_f32_tma<TI, TO, NC><<<grid, block, h.smem, stream>>>(h.map, kp, h.sp);
             return cudaGetLastError();
         }
@@ -589,12 +590,13 @@ constexpr int NF = MAXN - 1;
 // with selects -- 8 instead of 16 loads per pixel.  A rotated warp-wide load touches one 32-byte sector per lane whatever
 // its width, and the L1 tag stage is what bounds this kernel (l1tex 77 % with scalar loads).
 template <typename TI, typename TO, int NC, bool IDENT, bool STAGED, bool VEC = false>
-__device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char *stage, int spitch, int sox, int soy) {
+__device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char *stage, int spitch, int sox, int soy,
+                                          int tile_x, int tile_y) {
     static_assert(!STAGED || IDENT, "staging is implemented for identity addressing");
     static_assert(!VEC || (IDENT && !STAGED && NC == 1 && sizeof(TI) == 4), "vector loads: float, 1 channel, identity");
     constexpr int NV = (NF + 3 + 3) / 4;  // aligned float4 vectors that cover NF floats from any offset 0..3
-    const int x = blockIdx.x * TILE_W + threadIdx.x;
-    const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
+    const int x = tile_x * TILE_W + threadIdx.x;
+    const int y = kp.row0 + tile_y * TILE_H + threadIdx.y;
     if (x >= kp.dst_w || y >= kp.row1) return;
     const double cx = fma((double)x, kp.aff_xx, fma((double)y, kp.aff_xy, kp.aff_x0));
     const double cy = fma((double)x, kp.aff_yx, fma((double)y, kp.aff_yy, kp.aff_y0));
@@ -767,13 +769,13 @@ __device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char 
 template <typename TI, typename TO, int NC, bool IDENT>
 __global__ void __launch_bounds__(TILE_W *TILE_H, 1024 / (TILE_W * TILE_H))
     fast_kernel_f32u(const __grid_constant__ AaiKernelParams kp) {
-    fast_body<TI, TO, NC, IDENT, false>(kp, nullptr, 0, 0, 0);
+    fast_body<TI, TO, NC, IDENT, false>(kp, nullptr, 0, 0, 0, blockIdx.x, blockIdx.y);
 }
 // float images, one channel, identity addressing, 16-byte aligned rows: 128-bit loads (see fast_body)
 template <typename TO>
 __global__ void __launch_bounds__(TILE_W *TILE_H, 1024 / (TILE_W * TILE_H))
     fast_kernel_f32u_vec(const __grid_constant__ AaiKernelParams kp) {
-    fast_body<float, TO, 1, true, false, true>(kp, nullptr, 0, 0, 0);
+    fast_body<float, TO, 1, true, false, true>(kp, nullptr, 0, 0, 0, blockIdx.x, blockIdx.y);
 }
 
 // the same kernel with the CTA's source window staged through shared memory by TMA (AAI_ARITH_F32_STAGED).  Measured on
@@ -788,7 +790,77 @@ __global__ void __launch_bounds__(TILE_W *TILE_H, 1024 / (TILE_W * TILE_H))
     __shared__ int origin[2];
     int sox, soy;
     stage_window<(int)sizeof(TI), NC>(&tmap, kp, sp, stage_raw, &bar, origin, kp.shapef.hb + 4e-6f, sox, soy);
-    fast_body<TI, TO, NC, true, true>(kp, (const char *)stage_raw, sp.bw * (int)sizeof(TI), sox, soy);
+    fast_body<TI, TO, NC, true, true>(kp, (const char *)stage_raw, sp.bw * (int)sizeof(TI), sox, soy, blockIdx.x, blockIdx.y);
+}
+
+// The staged kernel made PERSISTENT (AAI_ARITH_F32_RING): a CTA walks over the canvas tiles blockIdx.x, + gridDim.x, ...
+// with TWO window buffers -- while the 128 threads evaluate tile k out of one buffer, the TMA load of tile k + 1 is in
+// flight into the other (one elected thread computes the next window origin and issues it; completion on one mbarrier per
+// buffer, phase = use count).  That removes what sank the one-shot staged kernel (every CTA waiting for its own load in
+// front of ~250 instructions per thread) and keeps its relief of the L1 tag stage (LDS instead of rotated LDGs).
+constexpr int RING_STAGES = 2;
+template <typename TI, typename TO, int NC>
+__global__ void __launch_bounds__(TILE_W *TILE_H, 1024 / (TILE_W * TILE_H))
+    fast_kernel_f32u_ring(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ AaiKernelParams kp,
+                          const StageParams sp, const int tiles_x, const int ntiles) {
+    extern __shared__ __align__(128) unsigned char stage_raw[];
+    __shared__ uint64_t full[RING_STAGES];
+    __shared__ int origin[RING_STAGES][2];
+    constexpr int EB = (int)sizeof(TI), EAL = 16 / EB;
+    const int tid = threadIdx.y * TILE_W + threadIdx.x;
+    const uint32_t stage_bytes = (uint32_t)(sp.bw * sp.bh * EB);
+    const uint32_t stage_stride = (stage_bytes + 127u) & ~127u;
+    const float ext = kp.shapef.hb + 4e-6f;
+    auto issue = [&](int t, int s) {  // one thread: window origin of tile t (FP64, extremes at the tile's corners), TMA
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        const int x0 = tx * TILE_W, y0 = kp.row0 + ty * TILE_H;
+        double lox = 1e300, loy = 1e300;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const double xx = (double)(x0 + (c & 1) * (TILE_W - 1)), yy = (double)(y0 + (c >> 1) * (TILE_H - 1));
+            lox = fmin(lox, fma(xx, kp.aff_xx, fma(yy, kp.aff_xy, kp.aff_x0)));
+            loy = fmin(loy, fma(xx, kp.aff_yx, fma(yy, kp.aff_yy, kp.aff_y0)));
+        }
+        int ex = (__double2int_rd(lox - (double)ext) - 1) * NC;
+        ex = (ex >= 0 ? ex / EAL : -((-ex + EAL - 1) / EAL)) * EAL;
+        const int ey = __double2int_rd(loy - (double)ext) - 1;
+        origin[s][0] = ex;
+        origin[s][1] = ey;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(st_smem_u32(&full[s])), "r"(stage_bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+                "r"(st_smem_u32(stage_raw + (size_t)s * stage_stride)),
+            "l"(&tmap), "r"(st_smem_u32(&full[s])), "r"(ex), "r"(ey - src_row0(kp))
+            : "memory");
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < RING_STAGES; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&full[s])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if ((int)blockIdx.x < ntiles) issue((int)blockIdx.x, 0);
+    }
+    int k = 0;
+    for (int t = (int)blockIdx.x; t < ntiles; t += (int)gridDim.x, ++k) {
+        const int s = k & 1;
+        __syncthreads();  // every thread is done with the other buffer (tile k - 1); origin[s] of this tile is visible
+        if (tid == 0 && t + (int)gridDim.x < ntiles) issue(t + (int)gridDim.x, s ^ 1);
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "RG_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra.uni RG_DONE;\n"
+            "bra.uni RG_WAIT;\n"
+            "RG_DONE:\n"
+            "}\n" ::"r"(st_smem_u32(&full[s])),
+            "r"((k >> 1) & 1)
+            : "memory");
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        fast_body<TI, TO, NC, true, true>(kp, (const char *)stage_raw + (size_t)s * stage_stride, sp.bw * EB, origin[s][0],
+                                          origin[s][1], tx, ty);
+    }
 }
 
 template <typename TI, typename TO, int NC>
@@ -799,8 +871,26 @@ cudaError_t launch_fast3(const AaiKernelParams &kp, cudaStream_t stream) {
     dim3 grid((kp.dst_w + TILE_W - 1) / TILE_W, (rows + TILE_H - 1) / TILE_H, kp.batch > 1 ? kp.batch : 1);
     if (kp.scale == 1 && kp.quadrant == 0) {
         StageHost h;
-        if (kp.staged && stage_prepare<TI, NC>(kp, (double)kp.shapef.hb + 1e-5, h)) {  // A/B variant (AAI_ARITH_F32_STAGED)
-            fast_kernel_f32u_tma<TI, TO, NC><<<grid, block, h.smem, stream>>>(h.map, kp, h.sp);
+        if ((kp.staged == 1 || kp.staged == 3) && stage_prepare<TI, NC>(kp, (double)kp.shapef.hb + 1e-5, h)) {
+            if (kp.staged == 3) {  // AAI_ARITH_F32_RING: persistent CTAs, two window buffers
+                int dev = 0, sms = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                const int tiles_x = (int)grid.x, ntiles = (int)(grid.x * grid.y);
+                const size_t smem = RING_STAGES * ((h.smem + 127) & ~(size_t)127);
+                const int per_sm = 1024 / (TILE_W * TILE_H);
+                const dim3 pgrid((unsigned)std::min(ntiles, sms * per_sm), 1, grid.z);
+                static thread_local int attr_dev = -1;  // two buffers of a wide window exceed the 48 KB default
+                if (attr_dev != dev) {
+                    const cudaError_t e = cudaFuncSetAttribute(fast_kernel_f32u_ring<TI, TO, NC>,
+                                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+                    if (e != cudaSuccess) return e;
+                    attr_dev = dev;
+                }
+                fast_kernel_f32u_ring<TI, TO, NC><<<pgrid, block, smem, stream>>>(h.map, kp, h.sp, tiles_x, ntiles);
+                return cudaGetLastError();
+            }
+            fast_kernel_f32u_tma<TI, TO, NC><<<grid, block, h.smem, stream>>>(h.map, kp, h.sp);  // AAI_ARITH_F32_STAGED
             return cudaGetLastError();
         }
         if constexpr (sizeof(TI) == 4 && NC == 1) {

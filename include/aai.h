@@ -74,7 +74,11 @@ enum {
      * footprint it lies in (aai_kernels_bin.cu).  Same inside decisions as the default canvas-side gather kernel, a
      * different FP32 summation order; bitwise reproducible across band partitions.  Measured slower than the gather
      * kernel on B200 (profiles/README.md), so it is not the default.  Identical to AAI_ARITH_F32 in the other modes. */
-    AAI_ARITH_F32_BINNED = 3
+    AAI_ARITH_F32_BINNED = 3,
+    /* AAI_ARITH_F32 with fast mode computed by the staged gather kernel made persistent: CTAs walk over the canvas tiles
+     * with two shared-memory window buffers, the TMA load of the next tile in flight while the current one is evaluated.
+     * Same arithmetic as AAI_ARITH_F32_STAGED.  Identical to AAI_ARITH_F32 in the other modes. */
+    AAI_ARITH_F32_RING = 4
 };
 
 /*

@@ -901,6 +901,12 @@ def test_tma_staged_overlap_kernel_is_bitwise_the_ldg_kernel(aai, oracle, w, h, 
     # through the FP64 path than the staged one does, so those may differ in the last bits)
     fa, fb = fast[aai.ARITH_F32].cpu().numpy(), fast[aai.ARITH_F32_STAGED].cpu().numpy()
     assert (fa == fb).mean() > 0.995 and f32_err(fa, fb, 4096.0).max() <= TOL_F32_REL
+    # the persistent, double-buffered form of the staged kernel (AAI_ARITH_F32_RING) runs the same code per tile
+    ring = torch.full((plan.dst_h, plan.dst_w) + tail, -1.0, dtype=torch.float32, device="cuda")
+    aai.run_device(plan, aai.tensor_image(src[1]), aai.tensor_image(ring), mode=aai.MODE_FAST, arith=aai.ARITH_F32_RING,
+                   stream=stream)
+    torch.cuda.synchronize()
+    assert torch.equal(ring, fast[aai.ARITH_F32_STAGED])
     # row bands (each band holds only its halo rows) and a stack of slices through the staged kernel
     bands = torch.full_like(outs[aai.ARITH_F32][0], -2.0)
     from area_average_interpolation_b200.sharding import all_bands

@@ -93,8 +93,11 @@ for (w, h, ratio, angle, iso) in ([] if args.skip_checks else CASES):
     torch.cuda.synchronize()
     s1 = run(plan, srcs[1].contiguous(), aai.ARITH_F32_BINNED)
     line += f" stack bitwise {bool(torch.equal(dsts[0], a) and torch.equal(dsts[1], s1))}"
+    ring, staged = run(plan, src, aai.ARITH_F32_RING), run(plan, src, aai.ARITH_F32_STAGED)
+    ring_ok = bool(torch.equal(ring, staged)) and int((ring == SENT).sum()) == 0
+    line += f" | ring == staged {ring_ok}"
     print(line, flush=True)
-    bad += nbad + holes
+    bad += nbad + holes + (0 if ring_ok else 1)
 
 if args.time:
     w = h = 16384
@@ -102,7 +105,8 @@ if args.time:
     plan = aai.make_plan(w, h, 1.0, 0.37, (8192.0, 8192.0), 17.3)
     dst = torch.empty((plan.dst_h, plan.dst_w), dtype=torch.float32, device=dev)
     si, di = aai.tensor_image(src), aai.tensor_image(dst)
-    for name, arith in [("bin", aai.ARITH_F32_BINNED), ("gather", aai.ARITH_F32), ("bin", aai.ARITH_F32_BINNED)]:
+    for name, arith in [("bin", aai.ARITH_F32_BINNED), ("gather", aai.ARITH_F32), ("staged", aai.ARITH_F32_STAGED),
+                        ("ring", aai.ARITH_F32_RING), ("gather", aai.ARITH_F32), ("ring", aai.ARITH_F32_RING)]:
         for _ in range(3):
             aai.run_device(plan, si, di, mode=aai.MODE_FAST, arith=arith, stream=st)
         torch.cuda.synchronize()

@@ -35,7 +35,7 @@ else:
     src = torch.rand((cfg["h"], cfg["w"]) + tail, dtype=torch.float32, device=dev) * 4096
 dst = torch.empty((plan.dst_h, plan.dst_w) + tail, dtype=src.dtype if args.dst == "same" else torch.float32, device=dev)
 si, di = aai.tensor_image(src), aai.tensor_image(dst)
-arith = {"f32": aai.ARITH_F32, "f32s": aai.ARITH_F32_STAGED, "f32b": aai.ARITH_F32_BINNED}.get(args.arith, aai.ARITH_F64)
+arith = {"f32": aai.ARITH_F32, "f32s": aai.ARITH_F32_STAGED, "f32b": aai.ARITH_F32_BINNED, "f32r": aai.ARITH_F32_RING}.get(args.arith, aai.ARITH_F64)
 st = torch.cuda.current_stream().cuda_stream
 if args.batch:
     srcs = torch.rand((args.batch, cfg["h"], cfg["w"]), dtype=torch.float32, device=dev) * 4096
