@@ -585,6 +585,9 @@ constexpr int NF = MAXN - 1;
 #ifndef AAI_FAST_PRED_LOADS
 #define AAI_FAST_PRED_LOADS 1  // multi-channel images: load only the inside cells (0: always load all candidates up front)
 #endif
+#ifndef AAI_FAST_SKIP_LOADS
+#define AAI_FAST_SKIP_LOADS 1  // 128-bit-load kernel: do not request rows / vectors beyond the last lattice row / column of the box
+#endif
 // VEC (float images, one channel, identity addressing, 16-byte aligned rows): the NF candidates of a row are read as
 // aligned 128-bit vectors (the 4 NV floats from the 16-byte boundary below the first candidate) and shifted into place
 // with selects -- 8 instead of 16 loads per pixel.  A rotated warp-wide load touches one 32-byte sector per lane whatever
@@ -655,12 +658,18 @@ __device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char 
             const int o = bx0 & 3;
             const char *rowp = (const char *)kp.src + (int64_t)(by0 - src_row0(kp)) * kp.src_pitch + (int64_t)(bx0 - o) * 4;
             float v[NF][NF];
+            // the lattice points of the box are columns bx0 .. bx1 and rows by0 .. by1 (often one fewer than NF): vectors
+            // and rows beyond them hold no inside cell and are not requested -- the kernel is bound by the L1 tag stage, and
+            // the predicates are known before the first load (config 4: 5.4 instead of 8 requests per pixel, 0.588 -> 0.540 ms;
+            // the scalar-load kernel of 8-bit images does not gain from the same predicates: config 2 17 -> 19 us)
+            const int last_col = o + (bx1 - bx0), last_row = by1 - by0;
 #pragma unroll
-            for (int r = 0; r < NF; ++r) {  // all vector loads first: NF * NV independent 128-bit loads in flight
+            for (int r = 0; r < NF; ++r) {  // all vector loads first: up to NF * NV independent 128-bit loads in flight
                 float w[4 * NV];
 #pragma unroll
                 for (int q = 0; q < NV; ++q) {
-                    const float4 t = __ldg(reinterpret_cast<const float4 *>(rowp) + q);
+                    const bool need = AAI_FAST_SKIP_LOADS ? (r <= last_row && 4 * q <= last_col) : true;
+                    const float4 t = need ? __ldg(reinterpret_cast<const float4 *>(rowp) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                     w[4 * q] = t.x;
                     w[4 * q + 1] = t.y;
                     w[4 * q + 2] = t.z;
@@ -677,13 +686,13 @@ __device__ __forceinline__ void fast_body(const AaiKernelParams &kp, const char 
 #pragma unroll
             for (int r = 0; r < NF; ++r) {
                 const float ry = ry0 + (float)r;
-                const float ur = -ry * g.sn, vr = ry * g.cs;
+                const float2 uvr = make_float2(-ry * g.sn, ry * g.cs), cssn = make_float2(g.cs, g.sn);
 #pragma unroll
                 for (int k = 0; k < NF; ++k) {
                     const float rx = rx0 + (float)k;
-                    const float mu = g.half - fabsf(fmaf(rx, g.cs, ur));
-                    const float mv = g.half - fabsf(fmaf(rx, g.sn, vr));
-                    const float m = fminf(mu, mv);
+                    // (u, v) in one packed FFMA2; min(h - |u|, h - |v|) = h - max(|u|, |v|) exactly (same subtraction)
+                    const float2 uv = __ffma2_rn(make_float2(rx, rx), cssn, uvr);
+                    const float m = g.half - fmaxf(fabsf(uv.x), fabsf(uv.y));
                     worst = fminf(worst, fabsf(m));
                     if (m >= 0.0f) {  // closed point-in-square (837-864); predicated adds, no branch
                         count += 1.0f;

@@ -332,8 +332,9 @@ class Bench:
         rank, world, local, dev, stream = self.rank, self.world, self.local, self.dev, self.stream
         if arith_name == "auto":
             arith = aai.ARITH_F64 if cfg["dtype"] == "float64" else aai.ARITH_F32
-        else:
-            arith = aai.ARITH_F32 if arith_name == "f32" else aai.ARITH_F64
+        else:  # f32b / f32r: the opt-in fast-mode kernels (source-side binning, persistent TMA ring), measured beside the default
+            arith = {"f32": aai.ARITH_F32, "f32b": aai.ARITH_F32_BINNED, "f32r": aai.ARITH_F32_RING}.get(arith_name,
+                                                                                                       aai.ARITH_F64)
         np_dt = np.dtype(cfg["dtype"])
         t_dt = {"uint8": torch.uint8, "float32": torch.float32, "float64": torch.float64}[cfg["dtype"]]
         out_dt = t_dt  # the canvas has the image's own element type (8-bit in -> 8-bit out, round half up)
@@ -508,7 +509,7 @@ class Bench:
                         "algorithmic": "each source byte read once + each canvas byte written once (SURVEY 8d)"}
         else:
             F = flops_per_covered_pixel(plan.side, plan.cos_t, plan.sin_t, CH)
-            f32 = arith == aai.ARITH_F32
+            f32 = arith != aai.ARITH_F64
             peak = self.fp32_nominal if f32 else self.fp64_nominal
             achieved = F * covered / world / (ms_step * 1e-3) / 1e12
             roofline = {"bound": "fp32" if f32 else "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -531,7 +532,7 @@ class Bench:
 
         res = {
             "workload": cfg["label"], "mode": {1: "area-average", 2: "fast"}[mode],
-            "dtype": "f32" if arith == aai.ARITH_F32 else "f64", "canvas": f"{plan.dst_w}x{plan.dst_h}",
+            "dtype": "f32" if arith != aai.ARITH_F64 else "f64", "canvas": f"{plan.dst_w}x{plan.dst_h}",
             "canvas_dtype": str(out_dt).replace("torch.", ""), "value": value, "unit": UNIT, "ms_per_step": ms_step,
             "steps": steps, "gpu_launches": int(launches), "roofline": roofline, "covered_pixels": covered,
             "timing": (f"inputs larger than L2 ({resident / 1e6:.0f} MB resident source per rank)" if resident > 130e6
@@ -563,7 +564,7 @@ class Bench:
         from area_average_interpolation_b200.synthetic import synthetic_image_torch
 
         np_dt = np.dtype(cfg["dtype"])
-        f32 = arith == aai.ARITH_F32
+        f32 = arith != aai.ARITH_F64
         ok, max_err, checked, same = True, 0.0, 0, None
         try:
             step()
@@ -664,9 +665,11 @@ def our_arm(args, cfg_id):
         k = max(3, min(args.steps, 10))
         todo = [(f"cfg{c}", c, "auto", 1) for c in sorted(CONFIGS) if c != cfg_id]
         todo += [(f"cfg{cfg_id}_f64", cfg_id, "f64", 1), (f"cfg{cfg_id}_fast", cfg_id, "auto", 2)]
+        if CONFIGS[cfg_id]["dtype"] == "float32" and CONFIGS[cfg_id]["ch"] == 1:  # the measured alternatives of fast mode
+            todo += [(f"cfg{cfg_id}_fast_binned", cfg_id, "f32b", 2), (f"cfg{cfg_id}_fast_ring", cfg_id, "f32r", 2)]
         for name, c, ar, mode in todo:
             try:
-                r = b.measure(c, arith_name=ar, mode=mode, steps=k, with_e2e=(b.world == 1),
+                r = b.measure(c, arith_name=ar, mode=mode, steps=k, with_e2e=(b.world == 1 and ar in ("auto", "f64")),
                               with_verify=not args.no_verify, with_clocks=True, tag=name)
                 r.pop("_plan")
                 r.pop("_info")

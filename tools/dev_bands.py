@@ -15,7 +15,10 @@ ap.add_argument("--config", type=int, default=4)
 ap.add_argument("--parts", type=int, nargs="+", default=[8])
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--json", default="", help="append per-band features + times as JSON lines (cost-model fit)")
+ap.add_argument("--lib", default="", help="another build of libaai_b200.so (A/B variants)")
 args = ap.parse_args()
+if args.lib:
+    aai.LIB_PATH = args.lib
 cfg = CONFIGS[args.config]
 dev = torch.device("cuda:0")
 plan = aai.make_plan(cfg["w"], cfg["h"], 1.0, cfg["ratio"], cfg["iso"], cfg["angle"])
