@@ -153,20 +153,33 @@ struct Walk {
     int cnt;         // and its length
     // shared-space addresses of this lane's slot in entry 0, minus MAGIC_BITS * stride: address = bits(key) * stride + base
     uint32_t sum_base, cnt_base;
+#ifdef AAI_BIN_CHECK  // developer build (tools/build_variant.sh bincheck -DAAI_BIN_CHECK=1): trap on a key outside the box
+    uint32_t nent_chk;
+    __device__ __forceinline__ void check(uint32_t b) const {
+        if (b - BIN_MAGIC_BITS > nent_chk) __trap();
+    }
+#else
+    __device__ __forceinline__ void check(uint32_t) const {}
+#endif
     __device__ __forceinline__ void init(const float *sums, const unsigned char *cnts, int slot, int nent) {
         cur = BIN_MAGIC + (float)nent;  // the spare entry
         sum = 0.0f;
         cnt = 0;
         sum_base = bin_smem_u32(sums + slot) - BIN_MAGIC_BITS * (uint32_t)(NS * 4);
         cnt_base = bin_smem_u32(cnts + slot) - BIN_MAGIC_BITS * (uint32_t)NS;
+#ifdef AAI_BIN_CHECK
+        nent_chk = (uint32_t)nent;
+#endif
     }
     __device__ __forceinline__ void flush() {
         const uint32_t b = __float_as_uint(cur);
+        check(b);
         asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.u8 [%2], %3;" ::"r"(sum_base + b * (NS * 4)), "f"(sum),
                      "r"(cnt_base + b * NS), "r"(cnt));
     }
     __device__ __forceinline__ void add(float key, float v) {
         const uint32_t b = __float_as_uint(cur);
+        check(b);
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.neu.f32 p, %0, %1;\n\t@p st.shared.f32 [%2], %3;\n\t@p st.shared.u8 [%4], %5;\n\t}" ::"f"(key),
             "f"(cur), "r"(sum_base + b * (NS * 4)), "f"(sum), "r"(cnt_base + b * NS), "r"(cnt));

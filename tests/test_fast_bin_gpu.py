@@ -123,6 +123,40 @@ def test_binning_kernel_is_bitwise_reproducible_across_bands_chunks_and_stacks(a
     assert torch.equal(stack[2], _fast(aai, plan, src[2].contiguous(), aai.ARITH_F32_BINNED))
 
 
+def test_binning_kernel_random_plans_agree_with_gather_kernel(aai):
+    """Seeded random geometry (ratio, angle, isocentre, odd sizes): box sizes, shear ranges, tile / image border cases the
+    hand-picked shapes may miss.  The gather kernel (checked against the oracle elsewhere) is the reference here: same
+    inside decisions, so the two may differ by FP32 summation order only, and no pixel may be left unwritten."""
+    import torch
+
+    rng = np.random.default_rng(20261018)
+    stream = torch.cuda.current_stream().cuda_stream
+    worst = 0.0
+    for case in range(40):
+        w, h = int(rng.integers(40, 900)), int(rng.integers(40, 700))
+        ratio = float(rng.uniform(0.26, 0.7))
+        angle = float(rng.uniform(3.5, 86.5))
+        iso = (float(rng.uniform(-20, w + 20)), float(rng.uniform(-20, h + 20)))
+        src = torch.from_numpy(rng.uniform(0.0, 4096.0, size=(h, w)).astype(np.float32)).cuda()
+        plan = aai.make_plan(w, h, 1.0, ratio, iso, angle)
+        if plan.dst_w * plan.dst_h > 4_000_000 or plan.dst_w * plan.dst_h == 0:
+            continue
+        got = _fast(aai, plan, src, aai.ARITH_F32_BINNED)
+        ref = _fast(aai, plan, src, aai.ARITH_F32)
+        assert int((got == SENTINEL).sum()) == 0, (case, w, h, ratio, angle, iso)
+        err = float(f32_err(got.cpu().numpy(), ref.cpu().numpy(), 4096.0).max())
+        assert err <= 2e-6, (case, w, h, ratio, angle, iso, err)
+        worst = max(worst, err)
+        if case % 8 == 0:  # two row bands over the whole source: bitwise the single launch
+            bands = torch.full_like(got, -2.0)
+            mid = plan.dst_h // 2
+            for r0, r1 in ((0, mid), (mid, plan.dst_h)):
+                aai.run_device(plan, aai.tensor_image(src), aai.tensor_image(bands), r0, r1, mode=aai.MODE_FAST,
+                               arith=aai.ARITH_F32_BINNED, stream=stream)
+            torch.cuda.synchronize()
+            assert torch.equal(bands, got), (case, w, h, ratio, angle, iso)
+
+
 def test_binning_kernel_8bit_canvas_and_padded_views(aai, oracle):
     """float source -> 8-bit canvas (round half up), and a source that is a column view of a wider array (pitch not a
     multiple of 16 bytes: the kernel only needs 4-byte alignment)."""
