@@ -100,6 +100,8 @@ int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
+void aai_count_extra_launches(int n) { g_launches.fetch_add(n); }
+
 void aai_set_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);

@@ -89,5 +89,7 @@ int aai_launch_overlap_f64_n6(const AaiKernelParams &kp, int src_dtype, int dst_
 int aai_launch_overlap_f64_n8(const AaiKernelParams &kp, int src_dtype, int dst_dtype, void *stream);
 
 void aai_set_error(const char *fmt, ...);
+// aai_launch_count() bookkeeping for launchers that start more than the one kernel the C ABI glue counts per call
+void aai_count_extra_launches(int n);
 
 #endif  // AAI_INTERNAL_H_

@@ -479,6 +479,7 @@ cudaError_t launch_bin(const AaiKernelParams &kp, const BinParams &bp, dim3 grid
     const int rows = kp.row1 - kp.row0;
     const dim3 bgrid(BD_PARTS, (rows + TILE_H - 1) / TILE_H, grid.z);
     fast_border_kernel<TO><<<bgrid, dim3(TILE_W, TILE_H), 0, stream>>>(kp, NS);
+    aai_count_extra_launches(1);  // two kernels per call (the glue counts one)
     return cudaGetLastError();
 }
 template <typename TO>

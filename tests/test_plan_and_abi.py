@@ -241,3 +241,22 @@ def test_header_is_plain_c_and_links_from_a_c_program(aai, tmp_path):
                     str(src), "-L" + libdir, "-laai_b200", "-Wl,-rpath," + libdir, "-o", exe], check=True)
     out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
     assert out.strip() == "0 256 256 Assumed X & Y resolution are same.|"
+
+
+def test_python_mirror_constants_equal_the_header_enums(aai, tmp_path):
+    """The ctypes mirror spells the header's enum values out by hand: compile include/aai.h and compare."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = {"AAI_MODE_AREA_AVERAGE": aai.MODE_AREA_AVERAGE, "AAI_MODE_FAST": aai.MODE_FAST,
+             "AAI_ARITH_F64": aai.ARITH_F64, "AAI_ARITH_F32": aai.ARITH_F32, "AAI_ARITH_F32_STAGED": aai.ARITH_F32_STAGED,
+             "AAI_ARITH_F32_BINNED": aai.ARITH_F32_BINNED, "AAI_ARITH_F32_RING": aai.ARITH_F32_RING,
+             "AAI_F64": aai.F64, "AAI_F32": aai.F32, "AAI_U8": aai.U8, "AAI_ERR_ARGUMENT": aai.ERR_ARGUMENT}
+    src = tmp_path / "enums.c"
+    src.write_text('#include <stdio.h>\n#include "aai.h"\nint main(void) {\n' +
+                   "".join(f'    printf("{n} %d\\n", (int){n});\n' for n in names) + "    return 0;\n}\n")
+    exe = str(tmp_path / "enums")
+    subprocess.run(["gcc", "-std=c99", "-I" + os.path.join(root, "include"), str(src), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    got = {line.split()[0]: int(line.split()[1]) for line in out.splitlines()}
+    assert got == {n: int(v) for n, v in names.items()}
