@@ -26,8 +26,11 @@ constexpr int MAXN = AAI_MAXN;
 #define AAI_F64_COOP 0  // 1: border pixels warp-cooperative as in the FP32 kernel.  Measured on BASELINE config 4: 3.603 ms against 3.351 ms for each lane alone (profiles/README.md) -- the FP64 kernel keeps the round-1 form
 #endif
 
+#ifndef AAI_F64_MIN_CTAS
+#define AAI_F64_MIN_CTAS (512 / (AAI_TILE_W * AAI_TILE_H))  // 4 CTAs of 128 threads per SM: 128 registers
+#endif
 template <typename TI, typename TO, int NC, bool IDENT>
-__global__ void __launch_bounds__(TILE_W *TILE_H, 512 / (TILE_W *TILE_H))
+__global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F64_MIN_CTAS)
     overlap_kernel_f64u(const __grid_constant__ AaiKernelParams kp) {
     // (no early return: every lane of a warp reaches the cooperative section below)
     const int x = blockIdx.x * TILE_W + threadIdx.x;
