@@ -24,6 +24,11 @@
 // (the closed test counts such a pixel in both footprints) the canvas pixels either side are flagged and evaluated by
 // the reference's own expression (pixel_fast_f64).  Canvas pixels whose candidate box is clipped by the image border,
 // and the empty ones beyond it, are written by fast_border_kernel (same launch sequence, disjoint pixels).
+//
+// Selected with AAI_ARITH_F32_BINNED, NOT the default: measured on B200 (profiles/r2_w_*) it reads HBM exactly once and
+// takes the load off L1 (l1tex 42 % against 89 %), but at ~27 instructions per SOURCE pixel plus the emit phase it
+// executes as many instructions as the gather kernel at a lower issue rate -- 0.66 ms against 0.54 ms on BASELINE config 4,
+// slower on every ratio / angle tried.
 #include <cuda.h>
 
 #include <cmath>
@@ -36,7 +41,7 @@ namespace {
 
 constexpr int BT_THREADS = 128;          // 4 warps
 constexpr int BT_W = BT_THREADS;         // source columns per tile: one per lane
-constexpr int BT_HX = 2;                 // halo columns either side: a footprint reaches hb <= 2.19 - 1/2 beyond its lattice point
+constexpr int BT_HX = 2;                 // halo columns either side: the candidate box lies within 2 of the nearest lattice point (hb < 2.5)
 constexpr int BT_CW = BT_W - 2 * BT_HX;  // core columns: the canvas pixels whose nearest lattice point lies there are OURS
 #ifndef AAI_BIN_ROWS
 #define AAI_BIN_ROWS 64
@@ -67,7 +72,6 @@ struct BinParams {
     double wmin_di, wmin_dj;   // corner of the loaded region with the smallest V - kappa U
     int box_rows;              // canvas rows the region can reach (= height without the shear)
     double umin_di, umin_dj, vmin_di, vmin_dj;  // corner of the loaded region with the smallest U resp. V (0 or BT_W / BT_R)
-    int nf;                // most lattice points per axis within hb of a footprint centre
 };
 
 template <typename T>
@@ -529,7 +533,6 @@ int aai_launch_fast_bin(const AaiKernelParams &kp, int src_dtype, int dst_dtype,
             bp.wmin_dj = wj < 0.0 ? (double)BT_R : 0.0;
         }
     }
-    bp.nf = nf;
     if (bp.pitch > 128) return (int)cudaErrorNotSupported;
     bp.emit_w = bp.pitch <= 64 ? 64 : 128;
     bp.axx = (float)kp.aff_xx;
@@ -544,8 +547,7 @@ int aai_launch_fast_bin(const AaiKernelParams &kp, int src_dtype, int dst_dtype,
     bp.bv = (float)bp.ivj;
     const int ns = nf <= 4 ? 4 : 8;
     const size_t smem = ((((size_t)bp.pitch * bp.height + 1) * (ns * 5 + 1)) + 15) & ~(size_t)15;
-    if (smem > 100 * 1024 || (int64_t)bp.pitch * bp.height >= (1 << 16) || kp.dst_pitch * (int64_t)bp.height >= (1LL << 31))
-        return (int)cudaErrorNotSupported;
+    if (smem > 100 * 1024 || (int64_t)bp.pitch * bp.height >= (1 << 16)) return (int)cudaErrorNotSupported;
     // guard band of the FP32 bin coordinate: four roundings at the magnitude of the box (<= 4 * 2^-24 * extent) plus the
     // FP32 increments (extent * 2^-24 each), doubled
     const double extent = fmax(128.0, 2.0 * (double)(bp.pitch > bp.box_rows ? bp.pitch : bp.box_rows));

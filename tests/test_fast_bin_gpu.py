@@ -8,7 +8,7 @@ against the default canvas-side gather kernel (AAI_ARITH_F32), which makes the s
 import numpy as np
 import pytest
 
-from common import TOL_F32_REL, f32_err, rel_err, TOL_F64_REL
+from common import TOL_F32_REL, f32_err
 
 pytestmark = pytest.mark.gpu
 
