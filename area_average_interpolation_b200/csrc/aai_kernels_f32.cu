@@ -223,10 +223,18 @@ bool stage_prepare(const AaiKernelParams &kp, double ext, StageHost &h) {
 //                 per source pixel, and each source pixel is loaded ONCE per canvas pixel
 enum { ADDR_GENERAL = 0, ADDR_IDENT = 1, ADDR_GROUPED = 2 };
 // stage / spitch / sox / soy: the CTA's staged source window (STAGED only): row pitch in bytes, origin in elements / rows
-template <typename TI, typename TO, int NC, int ADDR, bool STAGED>
+// PDL: the instantiation for SHORT launches (row bands of a multi-GPU partition, pipeline chunks, small images), launched
+// with the programmatic-stream-serialization attribute: it releases its dependents at once (the next launch's CTAs become
+// resident while this grid's last wave drains) and touches no global memory before griddepcontrol.wait, which returns
+// once the preceding grid has completed and flushed -- so any data dependence between consecutive launches is still
+// honoured.  Measured (profiles/r2_z_pdl_ab.txt): the 8 bands of config 4 0.1844 -> 0.1824 ms, config 2 38 -> 36 us; the
+// two instructions cost ~80 ns per CTA on long launches, and even behind a run-time flag 0.7 % of the whole-canvas
+// launch -- hence a separate instantiation, used below kPdlMaxCtas CTAs only.
+template <typename TI, typename TO, int NC, int ADDR, bool STAGED, bool PDL = false>
 __device__ __forceinline__ void overlap_body(const AaiKernelParams &kp, const char *stage, int spitch, int sox, int soy) {
     constexpr bool IDENT = ADDR == ADDR_IDENT, GROUPED = ADDR == ADDR_GROUPED;
     static_assert(!STAGED || IDENT, "staging is implemented for identity addressing");
+    if constexpr (PDL) asm volatile("griddepcontrol.launch_dependents;");
     // (no early return: every lane of a warp reaches the cooperative FP64 section at the end)
     const int x = blockIdx.x * TILE_W + threadIdx.x;
     const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
@@ -247,6 +255,7 @@ __device__ __forceinline__ void overlap_body(const AaiKernelParams &kp, const ch
     const int ncols = ix1 - ix0 + 1, nrows = jy1 - jy0 + 1;
     char *drow = (char *)kp.dst + (int64_t)(y - dst_row0(kp)) * kp.dst_pitch;
     const bool work = valid && ncols > 0 && nrows > 0;
+    if constexpr (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");  // above: address arithmetic only
     if (valid && !work) {  // footprint bounding box misses the image: the reference writes 0 (577)
 #pragma unroll
         for (int ch = 0; ch < NC; ++ch) store_f<TO>(drow, x * NC + ch, 0.0f);
@@ -512,10 +521,28 @@ __device__ __forceinline__ void overlap_body(const AaiKernelParams &kp, const ch
     }
 }
 
-template <typename TI, typename TO, int NC, int ADDR>
+template <typename TI, typename TO, int NC, int ADDR, bool PDL = false>
 __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
     overlap_kernel_f32(const __grid_constant__ AaiKernelParams kp) {
-    overlap_body<TI, TO, NC, ADDR, false>(kp, nullptr, 0, 0, 0);
+    overlap_body<TI, TO, NC, ADDR, false, PDL>(kp, nullptr, 0, 0, 0);
+}
+#ifndef AAI_PDL
+#define AAI_PDL 1
+#endif
+constexpr long long kPdlMaxCtas = 150000;
+template <typename TI, typename TO, int NC>
+cudaError_t launch_short_pdl(const AaiKernelParams &kp, dim3 grid, dim3 block, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, overlap_kernel_f32<TI, TO, NC, ADDR_IDENT, true>, kp);
 }
 
 // the same kernel with the CTA's source window staged through shared memory by TMA (see "STAGED variants" above)
@@ -543,6 +570,7 @@ cudaError_t launch3(const AaiKernelParams &kp, cudaStream_t stream) {
             overlap_kernel_f32_tma<TI, TO, NC><<<grid, block, h.smem, stream>>>(h.map, kp, h.sp);
             return cudaGetLastError();
         }
+        if (AAI_PDL && (long long)grid.x * grid.y * grid.z <= kPdlMaxCtas) return launch_short_pdl<TI, TO, NC>(kp, grid, block, stream);
         overlap_kernel_f32<TI, TO, NC, ADDR_IDENT><<<grid, block, 0, stream>>>(kp);
     } else if (MAXN == 4 && kp.scale >= MAXN - 1)
         overlap_kernel_f32<TI, TO, NC, (MAXN == 4 ? ADDR_GROUPED : ADDR_GENERAL)><<<grid, block, 0, stream>>>(kp);
