@@ -181,6 +181,10 @@ static int launch_rows(const aai_plan &plan, int mode, int arith, AaiKernelParam
     for (int64_t a = row0; a < row1; a += AAI_MAX_ROWS_PER_LAUNCH) {
         kp.row0 = (int32_t)a;
         kp.row1 = (int32_t)(a + AAI_MAX_ROWS_PER_LAUNCH < row1 ? a + AAI_MAX_ROWS_PER_LAUNCH : row1);
+        {  // CTA row order: towards the end of the launch where the rotated image covers more of the canvas rows
+            const int64_t n = kp.row1 - kp.row0, e = n / 8 > 64 ? 64 : (n / 8 > 0 ? n / 8 : 1);
+            kp.reverse_rows = aai_covered_pixels(&plan, kp.row0, kp.row0 + e) > aai_covered_pixels(&plan, kp.row1 - e, kp.row1) ? 1 : 0;
+        }
         int e;
         if (mode == AAI_MODE_FAST)
             e = aai_launch_fast(kp, arith, src_dtype, dst_dtype, stream);

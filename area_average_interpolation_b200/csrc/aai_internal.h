@@ -32,6 +32,7 @@ struct AaiKernelParams {
     int32_t staged;   // FP32 kernels: 1 = source window staged through shared memory by TMA (A/B variant),
                       // 2 = fast mode binned from the source side where aai_kernels_bin.cu applies (A/B variant),
                       // 3 = fast mode by the persistent, double-buffered staged kernel (A/B variant)
+    int32_t reverse_rows;  // host side only: the launcher of short FP32 overlap launches picks the bottom-up instantiation
     double reach;     // L*sqrt(2)/2 (search window, 426-429)
     double hb;        // h*(c+s): half extent of the footprint's axis-aligned bounding box
     int32_t mod_w, mod_h, dst_w, dst_h;

@@ -230,14 +230,19 @@ enum { ADDR_GENERAL = 0, ADDR_IDENT = 1, ADDR_GROUPED = 2 };
 // honoured.  Measured (profiles/r2_z_pdl_ab.txt): the 8 bands of config 4 0.1844 -> 0.1824 ms, config 2 38 -> 36 us; the
 // two instructions cost ~80 ns per CTA on long launches, and even behind a run-time flag 0.7 % of the whole-canvas
 // launch -- hence a separate instantiation, used below kPdlMaxCtas CTAs only.
-template <typename TI, typename TO, int NC, int ADDR, bool STAGED, bool PDL = false>
+template <typename TI, typename TO, int NC, int ADDR, bool STAGED, bool PDL = false, bool REV = false>
 __device__ __forceinline__ void overlap_body(const AaiKernelParams &kp, const char *stage, int spitch, int sox, int soy) {
     constexpr bool IDENT = ADDR == ADDR_IDENT, GROUPED = ADDR == ADDR_GROUPED;
     static_assert(!STAGED || IDENT, "staging is implemented for identity addressing");
     if constexpr (PDL) asm volatile("griddepcontrol.launch_dependents;");
     // (no early return: every lane of a warp reaches the cooperative FP64 section at the end)
     const int x = blockIdx.x * TILE_W + threadIdx.x;
-    const int y = kp.row0 + blockIdx.y * TILE_H + threadIdx.y;
+    // REV (short-launch instantiation only): CTA rows bottom-up.  A row band whose covered span narrows downwards -- the
+    // lower half of a rotated canvas -- measured 2 % slower top-down than bottom-up (config 4, 8 bands: 0.1824 vs 0.1787 ms,
+    // profiles/r2_zz_band_order.txt), so the launcher picks the direction in which the covered rows get wider.  A compile-
+    // time choice: as a run-time select the same arithmetic cost every launch 3.4 %.
+    const int by = REV ? (int)gridDim.y - 1 - (int)blockIdx.y : (int)blockIdx.y;
+    const int y = kp.row0 + by * TILE_H + threadIdx.y;
     const bool valid = x < kp.dst_w && y < kp.row1;
     // Footprint centre from the affine form of Source.cpp:212-219 (two FP64 FMAs per coordinate; within ~1e-12 of
     // the reference's own expression, pixel_centre(), which the FP64 redo path below evaluates), split into the nearest
@@ -521,10 +526,10 @@ __device__ __forceinline__ void overlap_body(const AaiKernelParams &kp, const ch
     }
 }
 
-template <typename TI, typename TO, int NC, int ADDR, bool PDL = false>
+template <typename TI, typename TO, int NC, int ADDR, bool PDL = false, bool REV = false>
 __global__ void __launch_bounds__(TILE_W *TILE_H, AAI_F32_MIN_BLOCKS)
     overlap_kernel_f32(const __grid_constant__ AaiKernelParams kp) {
-    overlap_body<TI, TO, NC, ADDR, false, PDL>(kp, nullptr, 0, 0, 0);
+    overlap_body<TI, TO, NC, ADDR, false, PDL, REV>(kp, nullptr, 0, 0, 0);
 }
 #ifndef AAI_PDL
 #define AAI_PDL 1
@@ -542,7 +547,8 @@ cudaError_t launch_short_pdl(const AaiKernelParams &kp, dim3 grid, dim3 block, c
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, overlap_kernel_f32<TI, TO, NC, ADDR_IDENT, true>, kp);
+    if (kp.reverse_rows) return cudaLaunchKernelEx(&cfg, overlap_kernel_f32<TI, TO, NC, ADDR_IDENT, true, true>, kp);
+    return cudaLaunchKernelEx(&cfg, overlap_kernel_f32<TI, TO, NC, ADDR_IDENT, true, false>, kp);
 }
 
 // the same kernel with the CTA's source window staged through shared memory by TMA (see "STAGED variants" above)

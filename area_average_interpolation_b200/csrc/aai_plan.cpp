@@ -188,16 +188,17 @@ int64_t aai_covered_pixels(const aai_plan *plan, int64_t row0, int64_t row1) {
 int aai_partition_rows(const aai_plan *plan, int n_parts, int64_t *bounds) {
     if (!plan || plan->status != AAI_OK || n_parts <= 0 || !bounds) return AAI_ERR_ARGUMENT;
     const int64_t h = plan->dst_h;
-    // weight of a row = covered pixels + 0.16 per canvas pixel outside the rotated image: an empty pixel still costs its
-    // centre / range set-up and its zero store, and rows near the canvas corners carry more partially covered warps and
-    // border pixels.  Fitted to per-band kernel times on B200 (tools/dev_bands.py, 2 / 4 / 8 / 16 bands, round 2, after
-    // the border pixels went warp-cooperative): t = a (covered + w empty) + 8 us per launch, w = 0.15 for BASELINE config 4
-    // and 0.20 for config 3, residual +-2 %.  The +1 keeps the split defined for fully empty canvases.
+    // weight of a row = covered pixels + 0.18 per canvas pixel outside the rotated image: an empty pixel still costs its
+    // centre / range set-up and its zero store (~150 instructions against 940 / 740 for a covered pixel of BASELINE config
+    // 4 / 3), and rows near the canvas corners carry more partially covered warps and border pixels.  Fitted to per-band
+    // kernel times on B200 (tools/dev_bands.py; final kernels of round 2, bands launched in the direction of growing covered
+    // rows): t = a (covered + w empty) + c per launch, w = 0.17 for config 4 and 0.20 for config 3.  The +1 keeps the split
+    // defined for fully empty canvases.
     std::vector<double> prefix((size_t)h + 1, 0.0);
     for (int64_t y = 0; y < h; ++y) {
         int64_t xa, xb;
         covered_span(*plan, y, xa, xb);
-        prefix[(size_t)y + 1] = prefix[(size_t)y] + (double)(xb - xa) + 0.16 * (double)(plan->dst_w - (xb - xa)) + 1.0;
+        prefix[(size_t)y + 1] = prefix[(size_t)y] + (double)(xb - xa) + 0.18 * (double)(plan->dst_w - (xb - xa)) + 1.0;
     }
     const double total = prefix[(size_t)h];
     bounds[0] = 0;

@@ -92,9 +92,9 @@ def test_partition_covers_canvas_and_balances_kernel_cost(aai):
         assert b[0] == 0 and b[-1] == p.dst_h and all(b[i] < b[i + 1] for i in range(n))
         loads = [aai.covered_pixels(p, b[i], b[i + 1]) for i in range(n)]
         assert sum(loads) == total
-        # the split equalises the measured cost model (covered pixels + 0.16 per empty canvas pixel, aai_plan.cpp), so
+        # the split equalises the measured cost model (covered pixels + 0.18 per empty canvas pixel, aai_plan.cpp), so
         # the bands at the canvas corners (many rows, short spans) hold fewer covered pixels than the middle ones
-        cost = [loads[i] + 0.16 * ((b[i + 1] - b[i]) * p.dst_w - loads[i]) for i in range(n)]
+        cost = [loads[i] + 0.18 * ((b[i + 1] - b[i]) * p.dst_w - loads[i]) for i in range(n)]
         assert max(cost) <= 1.01 * sum(cost) / n, (n, cost)
         assert max(loads) <= 1.10 * total / n, (n, loads)
 
