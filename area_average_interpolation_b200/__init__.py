@@ -83,6 +83,10 @@ def lib() -> C.CDLL:
         L.aai_last_error.restype = C.c_char_p
         L.aai_partition_rows.restype = C.c_int
         L.aai_partition_rows.argtypes = [C.POINTER(Plan), C.c_int, C.POINTER(C.c_int64)]
+        L.aai_partition_rows_weighted.restype = C.c_int
+        L.aai_partition_rows_weighted.argtypes = [C.POINTER(Plan), C.c_int, C.c_double, C.POINTER(C.c_int64)]
+        L.aai_band_empty_weight.restype = C.c_double
+        L.aai_band_empty_weight.argtypes = [C.POINTER(Plan), C.c_int, C.c_int]
         L.aai_band_source_window.restype = C.c_int
         L.aai_band_source_window.argtypes = [C.POINTER(Plan), C.c_int64, C.c_int64] + [C.POINTER(C.c_int64)] * 4
         L.aai_covered_pixels.restype = C.c_int64
@@ -185,9 +189,19 @@ def make_plan(src_w: int, src_h: int, src_resolution, dst_resolution, src_isocen
     return p
 
 
-def partition_rows(plan: Plan, n_parts: int) -> list:
+def band_empty_weight(plan: Plan, mode: int = MODE_AREA_AVERAGE, arith: int = ARITH_F32) -> float:
+    """``aai_band_empty_weight``: measured cost of an empty canvas pixel relative to a covered one for the kernel that
+    (mode, arith) selects on this plan."""
+    return float(lib().aai_band_empty_weight(C.byref(plan), int(mode), int(arith)))
+
+
+def partition_rows(plan: Plan, n_parts: int, empty_weight: Optional[float] = None) -> list:
+    """``aai_partition_rows`` (FP32 overlap kernel's weight) or, with ``empty_weight``, ``aai_partition_rows_weighted``."""
     b = (C.c_int64 * (n_parts + 1))()
-    _check(lib().aai_partition_rows(C.byref(plan), int(n_parts), b))
+    if empty_weight is None:
+        _check(lib().aai_partition_rows(C.byref(plan), int(n_parts), b))
+    else:
+        _check(lib().aai_partition_rows_weighted(C.byref(plan), int(n_parts), float(empty_weight), b))
     return list(b)
 
 

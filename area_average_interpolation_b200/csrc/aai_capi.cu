@@ -763,7 +763,7 @@ int aai_run_host(const aai_plan *plan, int mode, int arith, const aai_image *src
             return AAI_ERR_ARGUMENT;
         }
     std::vector<int64_t> bounds((size_t)n_devices + 1);
-    rc = aai_partition_rows(plan, n_devices, bounds.data());
+    rc = aai_partition_rows_weighted(plan, n_devices, aai_band_empty_weight(plan, mode, arith), bounds.data());
     if (rc != AAI_OK) return rc;
     if (n_devices == 1) return aai_run_host_band(plan, mode, arith, src, dst, 0, plan->dst_h, devices[0], nullptr, 1);
 

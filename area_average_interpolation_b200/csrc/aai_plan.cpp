@@ -185,20 +185,33 @@ int64_t aai_covered_pixels(const aai_plan *plan, int64_t row0, int64_t row1) {
     return total;
 }
 
+// Cost of an empty canvas pixel relative to a covered one.  An empty pixel still costs its centre / range set-up and its
+// zero store (~150 instructions), a covered one 940 (FP32 overlap kernel, BASELINE config 4), 740 (its upscaling path,
+// config 3), ~2650 (FP64 kernel) or ~330 (fast mode); rows near the canvas corners also carry more partially covered
+// warps and border pixels.  Fitted to per-band kernel times on B200, t = a (covered + w empty) + c per launch, with the
+// final kernels of round 2 (tools/dev_bands.py on one GPU; 8-GPU band times of profiles/r2_zz_scale_n8.json):
+// w = 0.17 (config 4: 0.166 ... 0.171), 0.20 (config 3), 0.06 (FP64 kernel), 0.27 (fast mode).
+double aai_band_empty_weight(const aai_plan *plan, int mode, int arith) {
+    if (mode == AAI_MODE_FAST) return 0.27;
+    if (arith == AAI_ARITH_F64) return 0.06;
+    return (plan && plan->scale >= 3) ? 0.20 : 0.17;
+}
+
 int aai_partition_rows(const aai_plan *plan, int n_parts, int64_t *bounds) {
-    if (!plan || plan->status != AAI_OK || n_parts <= 0 || !bounds) return AAI_ERR_ARGUMENT;
+    return aai_partition_rows_weighted(plan, n_parts, aai_band_empty_weight(plan, AAI_MODE_AREA_AVERAGE, AAI_ARITH_F32), bounds);
+}
+
+int aai_partition_rows_weighted(const aai_plan *plan, int n_parts, double empty_weight, int64_t *bounds) {
+    if (!plan || plan->status != AAI_OK || n_parts <= 0 || !bounds || !(empty_weight >= 0.0) || !(empty_weight <= 1.0))
+        return AAI_ERR_ARGUMENT;
     const int64_t h = plan->dst_h;
-    // weight of a row = covered pixels + 0.18 per canvas pixel outside the rotated image: an empty pixel still costs its
-    // centre / range set-up and its zero store (~150 instructions against 940 / 740 for a covered pixel of BASELINE config
-    // 4 / 3), and rows near the canvas corners carry more partially covered warps and border pixels.  Fitted to per-band
-    // kernel times on B200 (tools/dev_bands.py; final kernels of round 2, bands launched in the direction of growing covered
-    // rows): t = a (covered + w empty) + c per launch, w = 0.17 for config 4 and 0.20 for config 3.  The +1 keeps the split
-    // defined for fully empty canvases.
+    // weight of a row = covered pixels + empty_weight per canvas pixel outside the rotated image; the +1 keeps the split
+    // defined for fully empty canvases
     std::vector<double> prefix((size_t)h + 1, 0.0);
     for (int64_t y = 0; y < h; ++y) {
         int64_t xa, xb;
         covered_span(*plan, y, xa, xb);
-        prefix[(size_t)y + 1] = prefix[(size_t)y] + (double)(xb - xa) + 0.18 * (double)(plan->dst_w - (xb - xa)) + 1.0;
+        prefix[(size_t)y + 1] = prefix[(size_t)y] + (double)(xb - xa) + empty_weight * (double)(plan->dst_w - (xb - xa)) + 1.0;
     }
     const double total = prefix[(size_t)h];
     bounds[0] = 0;

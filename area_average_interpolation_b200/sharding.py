@@ -10,7 +10,7 @@ the peer group of the C ABI (``aai_peer_*`` in include/aai.h, ``PeerGroup`` in t
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 from . import Plan, band_source_window, covered_pixels, partition_rows
 
@@ -31,15 +31,17 @@ class Band:
         return self.row1 - self.row0
 
 
-def band_for_rank(plan: Plan, rank: int, world_size: int) -> Band:
-    bounds = partition_rows(plan, world_size)
+def band_for_rank(plan: Plan, rank: int, world_size: int, empty_weight: Optional[float] = None) -> Band:
+    """``empty_weight``: cost of an empty canvas pixel relative to a covered one (``band_empty_weight(plan, mode, arith)``
+    for the kernel that will run; default: the FP32 overlap kernel's)."""
+    bounds = partition_rows(plan, world_size, empty_weight)
     r0, r1 = bounds[rank], bounds[rank + 1]
     x0, x1, y0, y1 = band_source_window(plan, r0, r1)
     return Band(rank, r0, r1, x0, x1, y0, y1, covered_pixels(plan, r0, r1))
 
 
-def all_bands(plan: Plan, world_size: int) -> List[Band]:
-    return [band_for_rank(plan, r, world_size) for r in range(world_size)]
+def all_bands(plan: Plan, world_size: int, empty_weight: Optional[float] = None) -> List[Band]:
+    return [band_for_rank(plan, r, world_size, empty_weight) for r in range(world_size)]
 
 
 def batch_slice(n_images: int, rank: int, world_size: int) -> Tuple[int, int]:

@@ -349,7 +349,9 @@ class Bench:
         info = {}
 
         if cfg["batch"] == 1:
-            band = band_for_rank(plan, rank, world)
+            # bands balanced for THIS kernel (the peer group of the end-to-end leg partitions with the library default)
+            band = band_for_rank(plan, rank, world,
+                                 None if (world > 1 and with_e2e) else aai.band_empty_weight(plan, mode, arith))
             halo_rows = band.src_y1 - band.src_y0
             # this rank's source halo, generated directly in HBM (bit-identical to the host generator)
             dev_src = synthetic_image_torch(W, H, np_dt, seed, channels=CH, y0=band.src_y0, rows=max(halo_rows, 1),

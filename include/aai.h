@@ -131,9 +131,15 @@ const char *aai_last_error(void);
 
 /* ---- row-band partitioner (host logic, no GPU needed) ---------------------------------------- */
 
-/* Splits canvas rows [0, dst_h) into n_parts contiguous bands balanced by COVERED pixels (canvas corners of a
- * rotated image are empty).  bounds[0..n_parts] receives the band limits. */
+/* Splits canvas rows [0, dst_h) into n_parts contiguous bands balanced by kernel cost: covered pixels plus a fraction
+ * of the EMPTY ones (canvas corners of a rotated image are empty, but an empty pixel still costs its set-up and its zero
+ * store).  bounds[0..n_parts] receives the band limits.  aai_partition_rows() uses the fraction of the FP32 overlap
+ * kernel; aai_partition_rows_weighted() takes it from the caller, and aai_band_empty_weight() returns the fraction
+ * measured on B200 for the kernel that (mode, arith) selects on this plan (the FP64 kernel's covered pixels cost more,
+ * fast mode's less).  aai_run_host() partitions with the weight of its own (mode, arith). */
 int aai_partition_rows(const aai_plan *plan, int n_parts, int64_t *bounds);
+int aai_partition_rows_weighted(const aai_plan *plan, int n_parts, double empty_weight, int64_t *bounds);
+double aai_band_empty_weight(const aai_plan *plan, int mode, int arith);
 
 /* Source rows/columns (in ORIGINAL source coordinates, half-open) that canvas rows [row0,row1) can touch:
  * the band's halo. */

@@ -92,11 +92,24 @@ def test_partition_covers_canvas_and_balances_kernel_cost(aai):
         assert b[0] == 0 and b[-1] == p.dst_h and all(b[i] < b[i + 1] for i in range(n))
         loads = [aai.covered_pixels(p, b[i], b[i + 1]) for i in range(n)]
         assert sum(loads) == total
-        # the split equalises the measured cost model (covered pixels + 0.18 per empty canvas pixel, aai_plan.cpp), so
-        # the bands at the canvas corners (many rows, short spans) hold fewer covered pixels than the middle ones
-        cost = [loads[i] + 0.18 * ((b[i + 1] - b[i]) * p.dst_w - loads[i]) for i in range(n)]
+        # the split equalises the measured cost model (covered pixels + a fraction of the empty canvas pixels,
+        # aai_band_empty_weight), so the bands at the canvas corners (many rows, short spans) hold fewer covered pixels
+        w = aai.band_empty_weight(p, aai.MODE_AREA_AVERAGE, aai.ARITH_F32)
+        assert w == 0.17
+        cost = [loads[i] + w * ((b[i + 1] - b[i]) * p.dst_w - loads[i]) for i in range(n)]
         assert max(cost) <= 1.01 * sum(cost) / n, (n, cost)
         assert max(loads) <= 1.10 * total / n, (n, loads)
+        # the same for the kernels with cheaper / dearer covered pixels
+        for mode, arith in ((aai.MODE_FAST, aai.ARITH_F32), (aai.MODE_AREA_AVERAGE, aai.ARITH_F64)):
+            wk = aai.band_empty_weight(p, mode, arith)
+            bk = aai.partition_rows(p, n, wk)
+            assert bk[0] == 0 and bk[-1] == p.dst_h and all(bk[i] < bk[i + 1] for i in range(n))
+            lk = [aai.covered_pixels(p, bk[i], bk[i + 1]) for i in range(n)]
+            ck = [lk[i] + wk * ((bk[i + 1] - bk[i]) * p.dst_w - lk[i]) for i in range(n)]
+            assert max(ck) <= 1.01 * sum(ck) / n, (n, mode, arith, ck)
+    assert aai.band_empty_weight(p, aai.MODE_FAST, aai.ARITH_F32) > 0.17 > aai.band_empty_weight(p, aai.MODE_AREA_AVERAGE, aai.ARITH_F64)
+    with pytest.raises(aai.AaiError):
+        aai.partition_rows(p, 4, -0.5)
 
 
 def test_band_source_window_contains_every_pixel_the_oracle_reads(aai):

@@ -16,6 +16,8 @@ ap.add_argument("--parts", type=int, nargs="+", default=[8])
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--json", default="", help="append per-band features + times as JSON lines (cost-model fit)")
 ap.add_argument("--lib", default="", help="another build of libaai_b200.so (A/B variants)")
+ap.add_argument("--arith", default="f32", choices=["f32", "f64"])
+ap.add_argument("--mode", type=int, default=1, choices=[1, 2], help="1 area average, 2 fast mode")
 args = ap.parse_args()
 if args.lib:
     aai.LIB_PATH = args.lib
@@ -30,16 +32,18 @@ else:
 dst = torch.empty((plan.dst_h, plan.dst_w) + tail, dtype=torch.float32, device=dev)
 si, di = aai.tensor_image(src), aai.tensor_image(dst)
 st = torch.cuda.current_stream().cuda_stream
+ARITH = aai.ARITH_F32 if args.arith == "f32" else aai.ARITH_F64
+WEIGHT = aai.band_empty_weight(plan, args.mode, ARITH)
 
 
 def timed(r0, r1):
     for _ in range(3):
-        aai.run_device(plan, si, di, r0, r1, arith=aai.ARITH_F32, stream=st)
+        aai.run_device(plan, si, di, r0, r1, mode=args.mode, arith=ARITH, stream=st)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        aai.run_device(plan, si, di, r0, r1, arith=aai.ARITH_F32, stream=st)
+        aai.run_device(plan, si, di, r0, r1, mode=args.mode, arith=ARITH, stream=st)
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / args.steps
@@ -69,7 +73,7 @@ def features(r0, r1):
 whole = timed(0, plan.dst_h)
 print(f"whole canvas: {whole:.4f} ms")
 for n in args.parts:
-    b = aai.partition_rows(plan, n)
+    b = aai.partition_rows(plan, n, WEIGHT)
     ts = [timed(b[k], b[k + 1]) for k in range(n)]
     cov = [aai.covered_pixels(plan, b[k], b[k + 1]) for k in range(n)]
     print(f"{n} bands: rows {[b[k + 1] - b[k] for k in range(n)]}")
