@@ -667,7 +667,8 @@ def our_arm(args, cfg_id):
         k = max(3, min(args.steps, 10))
         todo = [(f"cfg{c}", c, "auto", 1) for c in sorted(CONFIGS) if c != cfg_id]
         todo += [(f"cfg{cfg_id}_f64", cfg_id, "f64", 1), (f"cfg{cfg_id}_fast", cfg_id, "auto", 2)]
-        if CONFIGS[cfg_id]["dtype"] == "float32" and CONFIGS[cfg_id]["ch"] == 1:  # the measured alternatives of fast mode
+        hc = CONFIGS[cfg_id]
+        if hc["dtype"] == "float32" and hc["ch"] == 1 and hc["batch"] == 1 and hc["angle"] % 90 != 0:  # the measured alternatives of fast mode
             todo += [(f"cfg{cfg_id}_fast_binned", cfg_id, "f32b", 2), (f"cfg{cfg_id}_fast_ring", cfg_id, "f32r", 2)]
         for name, c, ar, mode in todo:
             try:
